@@ -1,0 +1,129 @@
+"""Distributed synchronous SGD (layer L6): the tutorial's ``run(rank, size)``.
+
+Parity: train_dist.py:103-127 / tuto.md:283-303 --
+``torch.manual_seed(1234)``; ``partition_dataset()``; ``Net()``;
+``SGD(lr=0.01, momentum=0.5)``; 10 epochs; per batch
+zero_grad -> forward -> nll_loss -> backward -> average_gradients -> step;
+per epoch ``print('Rank ', rank, ', epoch ', epoch, ': ', mean_loss)``.
+
+Fixes: D4 (loss accumulated detached, on device, read once per epoch); replicas
+are made identical by an explicit parameter broadcast, not only by equal seeds.
+
+Engines:
+  * ``engine="torch"``  -- torch ops + ``average_gradients`` (CPU/gloo plumbing
+    path, BASELINE.json config #1; also runs on CUDA).
+  * ``engine="fused"``  -- the B200 path: one fused sm_100a forward+backward
+    kernel, one fused peer-memory all-reduce + SGD kernel, replayed as a CUDA
+    graph (``ops/convnet_fused.py``).  Default on CUDA.
+"""
+from __future__ import annotations
+
+import time
+from math import ceil
+from typing import Callable, Optional
+
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+
+from . import comm
+from .data import partition_dataset
+from .models.convnet import Net
+from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
+
+__all__ = ["run", "train", "TrainConfig"]
+
+
+class TrainConfig:
+    """Literal defaults of the reference, exposed as fields."""
+
+    def __init__(self, epochs: int = 10, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234,
+                 global_batch: int = 128, engine: str = "auto", device: Optional[str] = None,
+                 max_steps: Optional[int] = None, dataset=None, log: Callable[..., None] = print,
+                 p_drop: float = 0.5, checkpoint: Optional[str] = None, resume: Optional[str] = None):
+        self.epochs, self.lr, self.momentum, self.seed = epochs, lr, momentum, seed
+        self.global_batch, self.engine, self.device = global_batch, engine, device
+        self.max_steps, self.dataset, self.log, self.p_drop = max_steps, dataset, log, p_drop
+        self.checkpoint, self.resume = checkpoint, resume
+
+
+def _pick_device(cfg: TrainConfig) -> torch.device:
+    if cfg.device is not None:
+        return torch.device(cfg.device)
+    if torch.cuda.is_available() and comm.is_initialized() and \
+            "nccl" in str(torch.distributed.get_backend()):
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
+    """Run the training loop; returns a dict with per-epoch mean losses and timing."""
+    cfg = cfg or TrainConfig()
+    torch.manual_seed(cfg.seed)                                   # train_dist.py:105
+    device = _pick_device(cfg)
+    engine = cfg.engine
+    if engine == "auto":
+        engine = "fused" if device.type == "cuda" else "torch"
+    train_set, bsz = partition_dataset(cfg.dataset, global_batch=cfg.global_batch, seed=cfg.seed)
+    num_batches = ceil(len(train_set.dataset) / float(bsz))      # train_dist.py:112
+    if engine == "fused":
+        from .ops.convnet_fused import FusedTrainer
+        trainer = FusedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
+                               p_drop=cfg.p_drop)
+        if cfg.resume:
+            trainer.load_state_dict(torch.load(cfg.resume, map_location="cpu"))
+        step_fn, epoch_loss_fn, model = trainer.step, trainer.pop_loss_sum, trainer
+    else:
+        model = Net(cfg.p_drop).to(device)
+        if cfg.resume:
+            model.load_state_dict(torch.load(cfg.resume, map_location="cpu")["model"])
+        broadcast_parameters(model)
+        model._grad_bucket = GradBucket(list(model.parameters()))
+        optimizer = optim.SGD(model.parameters(), lr=cfg.lr, momentum=cfg.momentum)
+        acc = torch.zeros((), device=device)
+
+        def step_fn(data, target):
+            data = data.to(device, non_blocking=True)
+            target = target.to(device, non_blocking=True)
+            model._grad_bucket.zero_()                           # optimizer.zero_grad()
+            output = model(data)
+            loss = F.nll_loss(output, target)
+            acc.add_(loss.detach())                              # epoch_loss += loss (D4 fixed)
+            loss.backward()
+            average_gradients(model)
+            optimizer.step()
+
+        def epoch_loss_fn():
+            v = float(acc.item())
+            acc.zero_()
+            return v
+
+    history, steps, t0 = [], 0, time.perf_counter()
+    done = False
+    for epoch in range(cfg.epochs):
+        model.train()
+        nb = 0
+        for data, target in train_set:
+            step_fn(data, target)
+            steps += 1
+            nb += 1
+            if cfg.max_steps is not None and steps >= cfg.max_steps:
+                done = True
+                break
+        denom = num_batches if not done else max(nb, 1)
+        mean_loss = epoch_loss_fn() / denom
+        history.append(mean_loss)
+        cfg.log("Rank ", comm.get_rank(), ", epoch ", epoch, ": ", mean_loss)
+        if done:
+            break
+    elapsed = time.perf_counter() - t0
+    if cfg.checkpoint and comm.get_rank() == 0:
+        from .utils.checkpoint import save_checkpoint
+        save_checkpoint(cfg.checkpoint, model, steps=steps, history=history)
+    return {"loss": history, "steps": steps, "seconds": elapsed, "bsz": bsz,
+            "samples_per_s": steps * bsz * size / max(elapsed, 1e-9), "model": model}
+
+
+def run(rank: int, size: int):
+    """Distributed Synchronous SGD Example (train_dist.py:103)."""
+    return train(rank, size, TrainConfig())

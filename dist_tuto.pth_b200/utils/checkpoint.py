@@ -1,0 +1,43 @@
+"""Checkpoint / resume (absent from the reference).
+
+Rank 0 writes ``{"model": state_dict, "optim": ..., "steps": ..}`` atomically
+(tmp file + rename).  Works for ``nn.Module`` models and for the fused trainer
+(which exposes ``state_dict()`` over its flat fp32 parameter/momentum buffers
+using the reference's parameter names, so checkpoints interchange)."""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, Optional
+
+import torch
+
+__all__ = ["save_checkpoint", "load_checkpoint"]
+
+
+def save_checkpoint(path: str, model, optimizer=None, **extra: Any) -> str:
+    sd = model.state_dict()
+    if "model" in sd and isinstance(sd.get("model"), dict):   # fused trainer: already structured
+        blob: Dict[str, Any] = dict(sd)
+    else:
+        blob = {"model": {k: v.detach().cpu() for k, v in sd.items()}}
+    if optimizer is not None:
+        blob["optim"] = optimizer.state_dict()
+    blob.update(extra)
+    tmp = f"{path}.tmp.{os.getpid()}"
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    torch.save(blob, tmp)
+    os.replace(tmp, path)
+    return path
+
+
+def load_checkpoint(path: str, model=None, optimizer=None, map_location="cpu") -> Dict[str, Any]:
+    blob = torch.load(path, map_location=map_location)
+    if model is not None:
+        if hasattr(model, "load_state_dict"):
+            try:
+                model.load_state_dict(blob["model"])
+            except Exception:
+                model.load_state_dict(blob)
+    if optimizer is not None and "optim" in blob:
+        optimizer.load_state_dict(blob["optim"])
+    return blob

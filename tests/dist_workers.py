@@ -1,0 +1,199 @@
+"""Worker functions for the distributed-CPU tier (run in spawned processes, gloo @127.0.0.1)."""
+import torch
+import torch.nn.functional as F
+
+import dist_tuto.pth_b200 as b2
+from dist_tuto.pth_b200 import comm, ring
+from dist_tuto.pth_b200.data import SyntheticMNIST
+from dist_tuto.pth_b200.parallel.ddp import DistributedDataParallel, GradBucket
+
+
+def w_p2p(rank, size):
+    # blocking (tuto.md:82-91)
+    t = torch.zeros(1)
+    if rank == 0:
+        t += 1
+        b2.send(t, dst=1)
+    elif rank == 1:
+        b2.recv(t, src=0)
+    if rank in (0, 1):
+        assert t[0] == 1.0
+    # non-blocking (tuto.md:102-116)
+    t = torch.zeros(3)
+    req = None
+    if rank == 0:
+        t += 7
+        req = b2.isend(t, dst=1)
+    elif rank == 1:
+        req = b2.irecv(t, src=0)
+    if req is not None:
+        req.wait()
+        assert req.is_completed()
+        assert torch.equal(t, torch.full((3,), 7.0))
+    b2.barrier()
+
+
+def w_collectives(rank, size):
+    ops = {"SUM": (b2.reduce_op.SUM, lambda v: sum(v)),
+           "PRODUCT": (b2.reduce_op.PRODUCT, lambda v: torch.tensor(v).prod().item()),
+           "MAX": (b2.reduce_op.MAX, max), "MIN": (b2.reduce_op.MIN, min)}
+    vals = [float(r + 1) for r in range(size)]
+    for name, (op, fn) in ops.items():
+        t = torch.full((4,), float(rank + 1))
+        b2.all_reduce(t, op=op)
+        assert torch.allclose(t, torch.full((4,), float(fn(vals)))), name
+        t = torch.full((4,), float(rank + 1))
+        b2.reduce(t, dst=size - 1, op=op)
+        if rank == size - 1:
+            assert torch.allclose(t, torch.full((4,), float(fn(vals)))), name
+    # group=0 means WORLD as in 2017 (train_dist.py:99)
+    t = torch.ones(1)
+    b2.all_reduce(t, op=b2.reduce_op.SUM, group=0)
+    assert t[0] == size
+    # broadcast
+    t = torch.full((2,), float(rank))
+    b2.broadcast(t, src=1)
+    assert torch.equal(t, torch.ones(2))
+    # scatter (list given on every rank, tutorial-era style)
+    out = torch.zeros(2)
+    lst = [torch.full((2,), float(10 + r)) for r in range(size)]
+    b2.scatter(out, src=0, scatter_list=lst)
+    assert torch.equal(out, torch.full((2,), float(10 + rank)))
+    # gather as in ptp.py:21-28 (gather_list passed by every rank)
+    tl = [torch.zeros(1) for _ in range(size)]
+    b2.gather(torch.ones(1), dst=0, gather_list=tl, group=0)
+    s = sum(tl)[0]
+    assert s == (size if rank == 0 else 0)
+    # all_gather
+    tl = [torch.zeros(1) for _ in range(size)]
+    b2.all_gather(tl, torch.full((1,), float(rank)))
+    assert [int(x[0]) for x in tl] == list(range(size))
+    # new_group (tuto.md:180-185)
+    g = b2.new_group([0, 1])
+    t = torch.ones(1)
+    if rank in (0, 1):
+        b2.all_reduce(t, op=b2.reduce_op.SUM, group=g)
+        assert t[0] == 2.0
+    assert b2.get_world_size() == size and b2.get_rank() == rank
+    b2.barrier()
+
+
+def w_ring(rank, size):
+    # rank-dependent data catches defect D3 (reference returns 3/6/9 instead of 6/6/6)
+    send = torch.arange(6, dtype=torch.float32).view(2, 3) * (rank + 1)
+    keep = send.clone()
+    recv = torch.zeros(2, 3)
+    b2.allreduce(send, recv)
+    expect = torch.arange(6, dtype=torch.float32).view(2, 3) * sum(r + 1 for r in range(size))
+    assert torch.allclose(recv, expect), (rank, recv)
+    assert torch.equal(send, keep)                       # out-of-place (tuto.md:354)
+    for n in (1, 5, 64, 1000):
+        send = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))
+        recv = torch.empty(n)
+        ring.allreduce_chunked(send, recv)
+        ref = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(size))
+        assert torch.allclose(recv, ref, atol=1e-5), n
+    if size >= 3:
+        g = b2.new_group([0, 2])
+        if rank in (0, 2):
+            recv = torch.zeros(2)
+            b2.allreduce(torch.full((2,), float(rank + 1)), recv, group=g)
+            assert torch.equal(recv, torch.full((2,), 4.0))
+    b2.barrier()
+
+
+def _loss_grads(model, rank):
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn(8, 1, 28, 28, generator=g)
+    y = torch.randint(0, 10, (8,), generator=g)
+    model.zero_grad()
+    F.nll_loss(model(x), y).backward()
+
+
+def w_average_gradients(rank, size):
+    torch.manual_seed(1234)
+    model = b2.Net().eval()                               # eval: no dropout, deterministic oracle
+    _loss_grads(model, rank)
+    local = [p.grad.clone() for p in model.parameters()]
+    gathered = [[torch.zeros_like(g) for _ in range(size)] for g in local]
+    for g, lst in zip(local, gathered):
+        b2.all_gather(lst, g)
+    b2.average_gradients(model)                           # catches defect D1 (no communication)
+    for p, lst in zip(model.parameters(), gathered):
+        mean = sum(lst) / size
+        assert torch.allclose(p.grad, mean, atol=1e-6)
+    # bucketed path
+    _loss_grads(model, rank)
+    model._grad_bucket = GradBucket(list(model.parameters()))
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(model.parameters(), model._grad_bucket.views))
+    b2.average_gradients(model)
+    for p, lst in zip(model.parameters(), gathered):
+        assert torch.allclose(p.grad, sum(lst) / size, atol=1e-6)
+    del model._grad_bucket
+    # DDP wrapper, small cap -> several buckets; optimizer.zero_grad(set_to_none=True) tolerated
+    torch.manual_seed(99 + rank)                          # different init per rank: broadcast must fix it
+    m2 = b2.Net().eval()
+    ddp = DistributedDataParallel(m2, bucket_cap_bytes=4096)
+    assert len(ddp.buckets) > 2
+    ref0 = [torch.zeros_like(p) for p in m2.parameters()]
+    for p, r in zip(m2.parameters(), ref0):
+        r.copy_(p.detach())
+        b2.broadcast(r, src=0)
+        assert torch.equal(r, p.detach())
+    m3 = b2.Net().eval()
+    m3.load_state_dict({k: v.clone() for k, v in m2.state_dict().items()})
+    _loss_grads(m3, rank)
+    gathered = []
+    for p in m3.parameters():
+        lst = [torch.zeros_like(p.grad) for _ in range(size)]
+        b2.all_gather(lst, p.grad)
+        gathered.append(lst)
+    for it in range(2):
+        if it == 0:
+            ddp.zero_grad()
+        else:
+            for p in m2.parameters():
+                p.grad = None
+        g = torch.Generator().manual_seed(50 + rank)
+        x = torch.randn(8, 1, 28, 28, generator=g)
+        y = torch.randint(0, 10, (8,), generator=g)
+        F.nll_loss(ddp(x), y).backward()
+        b2.average_gradients(m2)
+        for p, lst in zip(m2.parameters(), gathered):
+            assert torch.allclose(p.grad, sum(lst) / size, atol=1e-6), it
+    b2.barrier()
+
+
+def w_train(rank, size):
+    ds = SyntheticMNIST(n=1024, seed=5)
+    logs = []
+    cfg = b2.TrainConfig(epochs=4, dataset=ds, engine="torch", device="cpu", lr=0.1,
+                         log=lambda *a: logs.append(a))
+    out = b2.train(rank, size, cfg)
+    assert out["bsz"] == 128 // size and len(out["loss"]) == 4
+    assert out["loss"][-1] < out["loss"][0] - 0.05
+    assert logs[0][0] == "Rank " and logs[0][1] == rank
+    # replicas stay bit-identical after training (sync SGD invariant)
+    for p in out["model"].parameters():
+        lst = [torch.zeros_like(p) for _ in range(size)]
+        b2.all_gather(lst, p.detach())
+        assert all(torch.equal(lst[0], t) for t in lst)
+    b2.barrier()
+
+
+def w_fail(rank, size):
+    if rank == 1:
+        raise ValueError("boom on rank 1")
+    import time
+    time.sleep(60)
+
+
+def w_hang(rank, size):
+    import time
+    time.sleep(60)
+
+
+def w_env(rank, size):
+    import os
+    assert os.environ["MASTER_ADDR"] == "127.0.0.1"
+    assert b2.get_world_size() == size
