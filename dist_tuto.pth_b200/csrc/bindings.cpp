@@ -1,0 +1,254 @@
+// Python bindings (pybind11 / torch extension) for the native runtime and the sm_100a kernels.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "loader.h"
+
+#define B2_MAX_RANKS 8
+struct PeerPtrs { void* p[B2_MAX_RANKS]; };
+struct SignalPadsH { uint32_t* pad[B2_MAX_RANKS]; };
+
+extern "C" {
+const char* b2_symm_last_error();
+int b2_symm_caps(int dev, int* caps);
+int b2_symm_granularity(int dev, int ndev, int want_multicast, size_t* gran);
+int b2_symm_create(int dev, size_t bytes, unsigned long long* handle, int* fd);
+int b2_symm_import(int fd, unsigned long long* handle);
+int b2_symm_map(int dev, unsigned long long handle, size_t bytes, size_t align, unsigned long long* ptr);
+int b2_symm_unmap(unsigned long long ptr, size_t bytes);
+int b2_symm_release(unsigned long long handle);
+int b2_mc_create(int ndev, size_t bytes, unsigned long long* handle, int* fd);
+int b2_mc_add_device(unsigned long long mc, int dev);
+int b2_mc_bind(unsigned long long mc, unsigned long long mem, size_t bytes);
+int b2_mc_unbind(unsigned long long mc, int dev, size_t bytes);
+int b2_ipc_alloc(size_t bytes, unsigned long long* ptr, unsigned char* handle64);
+int b2_ipc_open(const unsigned char* handle64, unsigned long long* ptr);
+int b2_ipc_close(unsigned long long ptr);
+int b2_ipc_free(unsigned long long ptr);
+
+int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const SignalPadsH* sig, void* mc, const void* src,
+                        int src_f32, void* dst, int dst_f32, size_t n_vec, float scale, int rank, int world,
+                        int max_blocks, cudaStream_t stream);
+int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t stream);
+int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
+                            unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
+                            int world, int zero_grads, cudaStream_t stream);
+int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
+                       cudaStream_t stream);
+size_t b2_convnet_smem_bytes();
+int b2_convnet_npar();
+int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
+                           float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
+                           unsigned long long seed, long long sample_base, int B, int training, int backward,
+                           float inv_bsz, float p_drop, int max_ctas, cudaStream_t stream);
+int b2_gemm_available();
+int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias, int M, int N, int K, int relu,
+                        int out_bf16, cudaStream_t stream);
+const char* b2_gemm_last_error();
+}
+
+namespace {
+
+void ck_symm(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + " failed (rc=" + std::to_string(rc) + "): " + b2_symm_last_error());
+}
+void ck_cuda(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc));
+}
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+PeerPtrs to_ptrs(const std::vector<unsigned long long>& v) {
+  TORCH_CHECK(v.size() <= B2_MAX_RANKS, "at most 8 ranks per symmetric world");
+  PeerPtrs p;
+  for (int i = 0; i < B2_MAX_RANKS; ++i) p.p[i] = i < (int)v.size() ? (void*)(uintptr_t)v[i] : nullptr;
+  return p;
+}
+SignalPadsH to_sig(const std::vector<unsigned long long>& v) {
+  TORCH_CHECK(v.size() <= B2_MAX_RANKS, "at most 8 ranks per symmetric world");
+  SignalPadsH s;
+  for (int i = 0; i < B2_MAX_RANKS; ++i) s.pad[i] = i < (int)v.size() ? (uint32_t*)(uintptr_t)v[i] : nullptr;
+  return s;
+}
+
+void check_cuda_contig(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous(), name, " must be a contiguous CUDA tensor");
+}
+
+torch::Tensor tensor_from_ptr(unsigned long long ptr, int64_t numel, py::object dtype, int device) {
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  auto opts = torch::TensorOptions().dtype(st).device(torch::kCUDA, device);
+  return torch::from_blob((void*)(uintptr_t)ptr, {numel}, [](void*) {}, opts);
+}
+
+struct LoaderPy {
+  std::unique_ptr<b2::NativeLoader> impl;
+  torch::Tensor images, labels;   // keep the dataset alive
+  std::vector<torch::Tensor> xs, ys;
+  LoaderPy(torch::Tensor images_, torch::Tensor labels_, torch::Tensor index, int64_t batch, int n_buffers,
+           bool shuffle, bool drop_last, bool raw_u8, double mean, double std, uint64_t seed, bool pin)
+      : images(images_.contiguous()), labels(labels_.contiguous()) {
+    TORCH_CHECK(!images.is_cuda() && images.scalar_type() == torch::kUInt8, "images: CPU uint8 tensor");
+    TORCH_CHECK(!labels.is_cuda() && labels.scalar_type() == torch::kInt64, "labels: CPU int64 tensor");
+    auto idx = index.to(torch::kInt64).contiguous();
+    std::vector<int64_t> iv(idx.data_ptr<int64_t>(), idx.data_ptr<int64_t>() + idx.numel());
+    const int64_t n = images.size(0);
+    const int64_t item = images.numel() / std::max<int64_t>(n, 1);
+    for (auto v : iv) TORCH_CHECK(v >= 0 && v < n, "index out of range");
+    impl = std::make_unique<b2::NativeLoader>(images.data_ptr<uint8_t>(), labels.data_ptr<int64_t>(), item, std::move(iv),
+                                              batch, n_buffers, shuffle, drop_last, raw_u8, (float)mean, (float)std,
+                                              seed, pin);
+    std::vector<int64_t> shape{batch, 1};
+    for (int d = 1; d < images.dim(); ++d) shape.push_back(images.size(d));
+    for (int i = 0; i < std::max(2, n_buffers); ++i) {
+      auto& s = impl->slot(i);
+      xs.push_back(torch::from_blob(s.x, shape, torch::TensorOptions().dtype(raw_u8 ? torch::kUInt8 : torch::kFloat32)));
+      ys.push_back(torch::from_blob(s.y, {batch}, torch::TensorOptions().dtype(torch::kInt64)));
+    }
+  }
+  py::object next() {
+    int64_t count = 0;
+    int slot;
+    {
+      py::gil_scoped_release nogil;
+      slot = impl->next(&count);
+    }
+    if (slot < 0) return py::none();
+    return py::make_tuple(xs[slot].narrow(0, 0, count), ys[slot].narrow(0, 0, count));
+  }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "dist_tuto.pth_b200 native runtime: symmetric memory, fused sm_100a kernels, native loader";
+
+  // ------------------------------------------------------------------ symmetric memory
+  m.def("symm_caps", [](int dev) { int c[3]; ck_symm(b2_symm_caps(dev, c), "symm_caps"); return std::vector<int>{c[0], c[1], c[2]}; });
+  m.def("symm_granularity", [](int dev, int ndev, bool mc) { size_t g = 0; ck_symm(b2_symm_granularity(dev, ndev, mc, &g), "granularity"); return g; });
+  m.def("symm_create", [](int dev, size_t bytes) { unsigned long long h; int fd; ck_symm(b2_symm_create(dev, bytes, &h, &fd), "symm_create"); return py::make_tuple(h, fd); });
+  m.def("symm_import", [](int fd) { unsigned long long h; ck_symm(b2_symm_import(fd, &h), "symm_import"); return h; });
+  m.def("symm_map", [](int dev, unsigned long long h, size_t bytes, size_t align) { unsigned long long p; ck_symm(b2_symm_map(dev, h, bytes, align, &p), "symm_map"); return p; });
+  m.def("symm_unmap", [](unsigned long long p, size_t bytes) { ck_symm(b2_symm_unmap(p, bytes), "symm_unmap"); });
+  m.def("symm_release", [](unsigned long long h) { ck_symm(b2_symm_release(h), "symm_release"); });
+  m.def("mc_create", [](int ndev, size_t bytes) { unsigned long long h; int fd; ck_symm(b2_mc_create(ndev, bytes, &h, &fd), "mc_create"); return py::make_tuple(h, fd); });
+  m.def("mc_add_device", [](unsigned long long mc, int dev) { ck_symm(b2_mc_add_device(mc, dev), "mc_add_device"); });
+  m.def("mc_bind", [](unsigned long long mc, unsigned long long mem, size_t bytes) { ck_symm(b2_mc_bind(mc, mem, bytes), "mc_bind"); });
+  m.def("mc_unbind", [](unsigned long long mc, int dev, size_t bytes) { ck_symm(b2_mc_unbind(mc, dev, bytes), "mc_unbind"); });
+  m.def("ipc_alloc", [](size_t bytes) {
+    unsigned long long p; unsigned char h[64];
+    ck_symm(b2_ipc_alloc(bytes, &p, h), "ipc_alloc");
+    return py::make_tuple(p, py::bytes(reinterpret_cast<const char*>(h), 64));
+  });
+  m.def("ipc_open", [](py::bytes handle) {
+    std::string s = handle;
+    TORCH_CHECK(s.size() == 64, "ipc handle must be 64 bytes");
+    unsigned long long p; ck_symm(b2_ipc_open(reinterpret_cast<const unsigned char*>(s.data()), &p), "ipc_open");
+    return p;
+  });
+  m.def("ipc_close", [](unsigned long long p) { b2_ipc_close(p); });
+  m.def("ipc_free", [](unsigned long long p) { b2_ipc_free(p); });
+  m.def("tensor_from_ptr", &tensor_from_ptr, "wrap device memory as a 1-D tensor (no ownership)");
+
+  // ------------------------------------------------------------------ collectives
+  m.def("allreduce", [](int variant, bool bf16, std::vector<unsigned long long> bufs, std::vector<unsigned long long> sigs,
+                        unsigned long long mc, c10::optional<torch::Tensor> src, c10::optional<torch::Tensor> dst,
+                        size_t n_vec, double scale, int rank, int world, int max_blocks) {
+    PeerPtrs b = to_ptrs(bufs); SignalPadsH s = to_sig(sigs);
+    const void* sp = nullptr; void* dp = nullptr; int sf = 0, df = 0;
+    if (src.has_value()) { check_cuda_contig(*src, "src"); sp = src->data_ptr(); sf = src->scalar_type() == torch::kFloat32 && bf16; }
+    if (dst.has_value()) { check_cuda_contig(*dst, "dst"); dp = dst->data_ptr(); df = dst->scalar_type() == torch::kFloat32 && bf16; }
+    ck_cuda(b2_allreduce_launch(variant, bf16, &b, &s, (void*)(uintptr_t)mc, sp, sf, dp, df, n_vec, (float)scale, rank,
+                                world, max_blocks, cur_stream()), "allreduce launch");
+  }, py::arg("variant"), py::arg("bf16"), py::arg("bufs"), py::arg("sigs"), py::arg("mc"), py::arg("src"), py::arg("dst"),
+     py::arg("n_vec"), py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("max_blocks") = 0);
+  m.def("barrier", [](std::vector<unsigned long long> sigs, int rank, int world) {
+    SignalPadsH s = to_sig(sigs);
+    ck_cuda(b2_barrier_launch(&s, rank, world, cur_stream()), "barrier launch");
+  });
+  m.def("allreduce_sgd", [](std::vector<unsigned long long> grads, std::vector<unsigned long long> sigs, torch::Tensor params,
+                            torch::Tensor momentum, c10::optional<torch::Tensor> step, double lr, double mu, double scale,
+                            int rank, int world, bool zero_grads) {
+    check_cuda_contig(params, "params"); check_cuda_contig(momentum, "momentum");
+    TORCH_CHECK(params.scalar_type() == torch::kFloat32 && momentum.scalar_type() == torch::kFloat32, "fp32 flat buffers");
+    TORCH_CHECK(params.numel() % 4 == 0 && params.numel() == momentum.numel(), "flat buffers must be padded to 4 elements");
+    PeerPtrs g = to_ptrs(grads); SignalPadsH s = to_sig(sigs);
+    unsigned long long* st = step.has_value() ? reinterpret_cast<unsigned long long*>(step->data_ptr()) : nullptr;
+    ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
+                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, cur_stream()), "allreduce_sgd launch");
+  });
+  m.def("sgd_flat", [](torch::Tensor p, torch::Tensor mom, torch::Tensor g, double lr, double mu, double wd, bool zero_grad) {
+    check_cuda_contig(p, "p"); check_cuda_contig(mom, "m"); check_cuda_contig(g, "g");
+    TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
+    TORCH_CHECK(p.numel() == g.numel() && p.numel() == mom.numel());
+    TORCH_CHECK(((uintptr_t)p.data_ptr() | (uintptr_t)mom.data_ptr() | (uintptr_t)g.data_ptr()) % 16 == 0, "16-byte aligned buffers");
+    ck_cuda(b2_sgd_flat_launch(p.data_ptr<float>(), mom.data_ptr<float>(), g.data_ptr<float>(), (size_t)p.numel(), (float)lr,
+                               (float)mu, (float)wd, zero_grad, cur_stream()), "sgd_flat launch");
+  });
+
+  // ------------------------------------------------------------------ fused ConvNet step
+  m.def("convnet_npar", [] { return b2_convnet_npar(); });
+  m.def("convnet_smem_bytes", [] { return b2_convnet_smem_bytes(); });
+  m.def("convnet_step", [](torch::Tensor params, c10::optional<torch::Tensor> grads, torch::Tensor x, torch::Tensor target,
+                           c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
+                           c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
+                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas) {
+    check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
+    TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
+    TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
+    const bool u8 = x.scalar_type() == torch::kUInt8;
+    TORCH_CHECK(u8 || x.scalar_type() == torch::kFloat32, "x: float32 (normalised) or uint8 (raw)");
+    const int B = (int)target.numel();
+    TORCH_CHECK(x.numel() == (int64_t)B * 784, "x must be [B,1,28,28]");
+    float* g = nullptr;
+    if (grads.has_value()) { check_cuda_contig(*grads, "grads"); TORCH_CHECK(grads->scalar_type() == torch::kFloat32 && grads->numel() >= b2_convnet_npar()); g = grads->data_ptr<float>(); }
+    float* la = loss_acc.has_value() ? loss_acc->data_ptr<float>() : nullptr;
+    float* lp = nullptr;
+    if (out_logp.has_value()) { TORCH_CHECK(out_logp->numel() == (int64_t)B * 10 && out_logp->scalar_type() == torch::kFloat32); lp = out_logp->data_ptr<float>(); }
+    float* mo = nullptr;
+    if (mask_out.has_value()) { TORCH_CHECK(mask_out->numel() == (int64_t)B * 70 && mask_out->scalar_type() == torch::kFloat32); mo = mask_out->data_ptr<float>(); }
+    const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
+    c10::cuda::CUDAGuard guard(params.device());
+    ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
+                                   la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
+                                   max_ctas, cur_stream()), "convnet_step launch");
+  }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
+     py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
+     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0);
+
+  // ------------------------------------------------------------------ tcgen05 GEMM
+  m.def("gemm_available", [] { return b2_gemm_available() != 0; });
+  m.def("gemm_bf16", [](torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> bias, bool relu, bool out_bf16) {
+    // C[M,N] = A[M,K] @ B[N,K]^T (+bias) (relu) ; A,B bf16 row-major (K contiguous)
+    check_cuda_contig(a, "a"); check_cuda_contig(b, "b");
+    TORCH_CHECK(a.scalar_type() == torch::kBFloat16 && b.scalar_type() == torch::kBFloat16, "bf16 operands");
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1), "A[M,K], B[N,K]");
+    const int M = (int)a.size(0), K = (int)a.size(1), N = (int)b.size(0);
+    TORCH_CHECK(K % 8 == 0, "K must be a multiple of 8 (16-byte rows for TMA)");
+    const float* bp = nullptr;
+    if (bias.has_value()) { TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kFloat32 && bias->numel() == N); bp = bias->data_ptr<float>(); }
+    auto c = torch::empty({M, N}, a.options().dtype(out_bf16 ? torch::kBFloat16 : torch::kFloat32));
+    c10::cuda::CUDAGuard guard(a.device());
+    int rc = b2_gemm_bf16_launch(a.data_ptr(), b.data_ptr(), c.data_ptr(), bp, M, N, K, relu, out_bf16, cur_stream());
+    if (rc != 0) throw std::runtime_error(std::string("gemm_bf16: ") + b2_gemm_last_error());
+    return c;
+  }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("relu") = false, py::arg("out_bf16") = true);
+
+  // ------------------------------------------------------------------ native loader
+  py::class_<LoaderPy>(m, "NativeLoader")
+      .def(py::init<torch::Tensor, torch::Tensor, torch::Tensor, int64_t, int, bool, bool, bool, double, double, uint64_t, bool>(),
+           py::arg("images"), py::arg("labels"), py::arg("index"), py::arg("batch"), py::arg("n_buffers") = 4,
+           py::arg("shuffle") = true, py::arg("drop_last") = false, py::arg("raw_u8") = false, py::arg("mean") = 0.1307,
+           py::arg("std") = 0.3081, py::arg("seed") = 1234, py::arg("pin") = false)
+      .def("num_batches", [](LoaderPy& l) { return l.impl->num_batches(); })
+      .def("start_epoch", [](LoaderPy& l, int64_t e) { py::gil_scoped_release nogil; l.impl->start_epoch(e); })
+      .def("next", &LoaderPy::next)
+      .def("release", [](LoaderPy& l) { l.impl->release(); })
+      .def("stop", [](LoaderPy& l) { py::gil_scoped_release nogil; l.impl->stop(); });
+}

@@ -1,0 +1,451 @@
+// Fused MNIST-ConvNet training step for sm_100a: forward + loss + backward of the tutorial's `Net`
+// (train_dist.py:53-71, nll_loss train_dist.py:120, backward :122) in ONE kernel.
+//
+// The reference runs ~35 library/ATen kernels per step (cuDNN convs, pools, relus, dropouts, cuBLAS
+// linears, log_softmax, nll, and their backward twins) on [B,...] tensors that round-trip through
+// HBM.  The network is per-sample independent and tiny (21,840 parameters, < 8 KB of activations per
+// sample), so here one CTA carries a sample through the whole network and back with everything in
+// shared memory / registers; weight gradients are accumulated in shared memory and flushed once per
+// CTA with vectorised `red.global.add.v4.f32` into the flat gradient bucket -- which is the symmetric
+// buffer the fused all-reduce + SGD kernel (sgd.cu) reads over NVSwitch.  HBM traffic per step is the
+// input batch + one pass over the parameters; launches per step: 1 (+1 for all-reduce/SGD).
+//
+// Flat parameter layout (fp32, every tensor padded to 4 elements so all flushes are 16-byte vectors):
+//   conv1.w 0 | conv1.b 252 | conv2.w 264 | conv2.b 5264 | fc1.w 5284 | fc1.b 21284 | fc2.w 21336 |
+//   fc2.b 21836 | total 21848
+#include <cstdio>
+#include "common.cuh"
+
+namespace cn {
+
+constexpr int W1 = 0, B1 = 252, W2 = 264, B2 = 5264, W3 = 5284, B3 = 21284, W4 = 21336, B4 = 21836;
+constexpr int NPAR = 21848;
+constexpr int T = 256;
+
+struct __align__(16) Smem {
+  float w1[252];
+  float b1[12];
+  float w2f[250 * 20];      // [ci][ky][kx][co]          forward: 4 output channels per float4
+  float w2b[500 * 16];      // [co][ky][kx][half][8]     backward-data: 5 input channels per (half)
+  float b2[20];
+  float w4[500];
+  float b4[12];
+  float x[784];
+  float p1[1440];           // relu(pool(conv1))  [10][12][12]
+  float part[3 * 1440];     // conv2 partial sums [3][20][64] (3840 used) / dgrad partials [3][10][144]
+  float dc2pad[20 * 256];   // conv2-output gradient, zero padded [20][16][16]
+  float p2[320];            // relu(pool(drop(conv2)))  [20][4][4]
+  float g2[320];            // gradient at the pooled conv2 argmax
+  float g1[1440];           // gradient at the pooled conv1 argmax
+  float h[52];              // fc1 activation after relu+dropout
+  float hm[52];             // fc1 backward mask (relu' * dropout scale)
+  float dh[52];
+  float dlog[12];
+  float m2[20];             // dropout2d channel scale
+  float rnd[72];            // uniforms: [0,20) dropout2d, [20,70) dropout
+  float g[NPAR];            // per-CTA gradient accumulators
+  unsigned char a1[1440];   // conv1 pool argmax (0..3)
+  unsigned char a2[320];    // conv2 pool argmax (0..3)
+  float loss_local;
+  int correct_local;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct Args {
+  const float* params;      // flat fp32 [NPAR]
+  float* grads;             // flat fp32 [NPAR], accumulated with red.add (caller keeps it zeroed)
+  const void* x;            // [B,1,28,28] fp32 (normalised) or uint8 (raw, normalised here)
+  const long long* target;  // [B]
+  float* loss_acc;          // [0] += sum_b nll_b * inv_bsz ; [1] += #correct   (may be null)
+  float* out_logp;          // [B,10] log-probabilities (may be null)
+  float* mask_out;          // [B,70] dropout scales actually applied (debug/tests; may be null)
+  const unsigned long long* step;   // device step counter (RNG offset); may be null -> 0
+  unsigned long long seed;
+  long long sample_base;    // global index of sample 0 (rank * bsz): decorrelates ranks
+  int B;
+  int x_u8;
+  int training;             // dropout on/off
+  int backward;             // compute gradients
+  float inv_bsz;            // 1 / local batch (nll_loss mean)
+  float p_drop;
+  float mean, inv_std;      // uint8 normalisation
+};
+
+__global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const float* __restrict__ P = a.params;
+
+  // ---------------------------------------------------------------- P0: stage weights, zero accumulators
+  for (int i = tid; i < 250; i += T) s.w1[i] = P[W1 + i];
+  if (tid < 10) { s.b1[tid] = P[B1 + tid]; s.b4[tid] = P[B4 + tid]; }
+  if (tid < 20) s.b2[tid] = P[B2 + tid];
+  for (int i = tid; i < 500; i += T) s.w4[i] = P[W4 + i];
+  for (int i = tid; i < 5000; i += T) {         // conv2.weight [co][ci][ky][kx]
+    const float w = P[W2 + i];
+    const int co = i / 250, r = i % 250, ci = r / 25, k = r % 25;
+    s.w2f[(ci * 25 + k) * 20 + co] = w;
+    s.w2b[((co * 25 + k) * 2 + ci / 5) * 8 + ci % 5] = w;
+  }
+  if (a.backward)
+    for (int i = tid; i < NPAR; i += T) s.g[i] = 0.f;
+  if (tid == 0) { s.loss_local = 0.f; s.correct_local = 0; }
+  const unsigned long long step = a.step ? *a.step : 0ull;
+  const float keep_scale = 1.f / (1.f - a.p_drop);
+  __syncthreads();
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    // -------------------------------------------------------------- S0: input, RNG, clear scratch
+    if (a.x_u8) {
+      const unsigned char* xs = reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * 784;
+      for (int i = tid; i < 784; i += T) s.x[i] = ((float)xs[i] * (1.f / 255.f) - a.mean) * a.inv_std;
+    } else {
+      const float* xs = reinterpret_cast<const float*>(a.x) + (size_t)b * 784;
+      for (int i = tid; i < 784; i += T) s.x[i] = xs[i];
+    }
+    if (tid < 18) {
+      uint4 r = b2::Philox::gen(a.seed, (unsigned long long)(a.sample_base + b), step * 32ull + tid);
+      const float k = 2.3283064365386963e-10f;   // 2^-32
+      s.rnd[tid * 4 + 0] = r.x * k; s.rnd[tid * 4 + 1] = r.y * k;
+      s.rnd[tid * 4 + 2] = r.z * k; s.rnd[tid * 4 + 3] = r.w * k;
+    }
+    if (a.backward)
+      for (int i = tid; i < 20 * 256; i += T) s.dc2pad[i] = 0.f;
+    __syncthreads();
+
+    // -------------------------------------------------------------- S1: conv1 -> maxpool2 -> relu
+    for (int o = tid; o < 1440; o += T) {
+      const int c = o / 144, r = o % 144, py = r / 12, px = r % 12;
+      float patch[6][6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) patch[i][j] = s.x[(2 * py + i) * 28 + 2 * px + j];
+      const float bias = s.b1[c];
+      float a00 = bias, a01 = bias, a10 = bias, a11 = bias;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const float w = s.w1[c * 25 + ky * 5 + kx];
+          a00 = fmaf(w, patch[ky][kx], a00);
+          a01 = fmaf(w, patch[ky][kx + 1], a01);
+          a10 = fmaf(w, patch[ky + 1][kx], a10);
+          a11 = fmaf(w, patch[ky + 1][kx + 1], a11);
+        }
+      float m = a00; int arg = 0;
+      if (a01 > m) { m = a01; arg = 1; }
+      if (a10 > m) { m = a10; arg = 2; }
+      if (a11 > m) { m = a11; arg = 3; }
+      s.p1[o] = fmaxf(m, 0.f);
+      s.a1[o] = (unsigned char)arg;
+    }
+    if (tid < 20)
+      s.m2[tid] = a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
+    __syncthreads();
+
+    // -------------------------------------------------------------- S2: conv2 partial sums (K split 3)
+    if (tid < 240) {
+      const int cell = tid & 15, cg = (tid >> 4) % 5, ks = tid / 80;
+      const int py = cell >> 2, px = cell & 3;
+      const int ci0 = (ks == 0) ? 0 : (ks == 1 ? 4 : 7), ci1 = (ks == 0) ? 4 : (ks == 1 ? 7 : 10);
+      float acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+      for (int ci = ci0; ci < ci1; ++ci) {
+        float patch[6][6];
+        const float* src = &s.p1[ci * 144 + (2 * py) * 12 + 2 * px];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) patch[i][j] = src[i * 12 + j];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(&s.w2f[((ci * 5 + ky) * 5 + kx) * 20 + cg * 4]);
+            const float i00 = patch[ky][kx], i01 = patch[ky][kx + 1], i10 = patch[ky + 1][kx], i11 = patch[ky + 1][kx + 1];
+            acc[0][0] = fmaf(w.x, i00, acc[0][0]); acc[0][1] = fmaf(w.y, i00, acc[0][1]);
+            acc[0][2] = fmaf(w.z, i00, acc[0][2]); acc[0][3] = fmaf(w.w, i00, acc[0][3]);
+            acc[1][0] = fmaf(w.x, i01, acc[1][0]); acc[1][1] = fmaf(w.y, i01, acc[1][1]);
+            acc[1][2] = fmaf(w.z, i01, acc[1][2]); acc[1][3] = fmaf(w.w, i01, acc[1][3]);
+            acc[2][0] = fmaf(w.x, i10, acc[2][0]); acc[2][1] = fmaf(w.y, i10, acc[2][1]);
+            acc[2][2] = fmaf(w.z, i10, acc[2][2]); acc[2][3] = fmaf(w.w, i10, acc[2][3]);
+            acc[3][0] = fmaf(w.x, i11, acc[3][0]); acc[3][1] = fmaf(w.y, i11, acc[3][1]);
+            acc[3][2] = fmaf(w.z, i11, acc[3][2]); acc[3][3] = fmaf(w.w, i11, acc[3][3]);
+          }
+      }
+      // part[ks][co][cell][pos]  (pos = dy*2+dx inside the pool window)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(&s.part[ks * 1440 + ((cg * 4 + c) * 16 + cell) * 4]) =
+            make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S2b: +bias, dropout2d, maxpool2, relu
+    for (int o = tid; o < 320; o += T) {
+      const int co = o >> 4;
+      const float4 q0 = *reinterpret_cast<const float4*>(&s.part[o * 4]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&s.part[1440 + o * 4]);
+      const float4 q2 = *reinterpret_cast<const float4*>(&s.part[2880 + o * 4]);
+      const float bias = s.b2[co], sc = s.m2[co];
+      const float v0 = (q0.x + q1.x + q2.x + bias) * sc, v1 = (q0.y + q1.y + q2.y + bias) * sc;
+      const float v2 = (q0.z + q1.z + q2.z + bias) * sc, v3 = (q0.w + q1.w + q2.w + bias) * sc;
+      float m = v0; int arg = 0;
+      if (v1 > m) { m = v1; arg = 1; }
+      if (v2 > m) { m = v2; arg = 2; }
+      if (v3 > m) { m = v3; arg = 3; }
+      s.p2[o] = fmaxf(m, 0.f);
+      s.a2[o] = (unsigned char)arg;
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S3: fc1 + relu + dropout
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int j = (tid >> 3) + 32 * pass, l8 = tid & 7;
+      float sum = 0.f;
+      if (j < 50) {
+        const float4* wrow = reinterpret_cast<const float4*>(P + W3 + j * 320);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const float4 w = __ldg(wrow + l8 + 8 * k);
+          const float4 v = *reinterpret_cast<const float4*>(&s.p2[(l8 + 8 * k) * 4]);
+          sum = fmaf(w.x, v.x, sum); sum = fmaf(w.y, v.y, sum);
+          sum = fmaf(w.z, v.z, sum); sum = fmaf(w.w, v.w, sum);
+        }
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (j < 50 && l8 == 0) {
+        const float pre = sum + __ldg(P + B3 + j);
+        const float dm = a.training ? (s.rnd[20 + j] >= a.p_drop ? keep_scale : 0.f) : 1.f;
+        s.h[j] = fmaxf(pre, 0.f) * dm;
+        s.hm[j] = pre > 0.f ? dm : 0.f;
+      }
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S4: fc2 + log_softmax + nll
+    if (tid < 32) {
+      const long long y = a.target[b];
+      float logit = -INFINITY;
+      if (tid < 10) {
+        float acc = s.b4[tid];
+#pragma unroll 10
+        for (int i = 0; i < 50; ++i) acc = fmaf(s.w4[tid * 50 + i], s.h[i], acc);
+        logit = acc;
+      }
+      float mx = logit; int am = tid;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, mx, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, am, d);
+        if (o > mx || (o == mx && oi < am)) { mx = o; am = oi; }
+      }
+      float e = tid < 10 ? __expf(logit - mx) : 0.f;
+      float se = e;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+      const float lse = mx + __logf(se);
+      if (tid < 10) {
+        const float logp = logit - lse;
+        if (a.out_logp) a.out_logp[(size_t)b * 10 + tid] = logp;
+        s.dlog[tid] = (e / se - (tid == (int)y ? 1.f : 0.f)) * a.inv_bsz;
+        if (tid == (int)y) s.loss_local += -logp;
+      }
+      if (tid == 0 && am == (int)y) s.correct_local += 1;
+    }
+    if (a.mask_out) {
+      if (tid < 20) a.mask_out[(size_t)b * 70 + tid] = s.m2[tid];
+      else if (tid < 70) a.mask_out[(size_t)b * 70 + tid] =
+          a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
+    }
+    __syncthreads();
+    if (!a.backward) continue;
+
+    // -------------------------------------------------------------- S5: fc2 backward
+    for (int e = tid; e < 500; e += T) s.g[W4 + e] += s.dlog[e / 50] * s.h[e % 50];
+    if (tid < 10) s.g[B4 + tid] += s.dlog[tid];
+    if (tid >= 64 && tid < 114) {
+      const int i = tid - 64;
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) d = fmaf(s.w4[k * 50 + i], s.dlog[k], d);
+      s.dh[i] = d * s.hm[i];
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S6: fc1 backward
+    {
+      int j = 0, i = tid;                         // e = j*320 + i, e = tid + 256*m
+      for (int e = tid; e < 16000; e += T) {
+        s.g[W3 + e] += s.dh[j] * s.p2[i];
+        i += T;
+        if (i >= 320) { i -= 320; ++j; }
+      }
+      if (tid < 50) s.g[B3 + tid] += s.dh[tid];
+      for (int o = tid; o < 320; o += T) {
+        float d = 0.f;
+#pragma unroll 10
+        for (int jj = 0; jj < 50; ++jj) d = fmaf(__ldg(P + W3 + jj * 320 + o), s.dh[jj], d);
+        const int co = o >> 4, cell = o & 15, arg = s.a2[o];
+        const float gv = s.p2[o] > 0.f ? d * s.m2[co] : 0.f;
+        s.g2[o] = gv;
+        const int y = 2 * (cell >> 2) + (arg >> 1), x = 2 * (cell & 3) + (arg & 1);
+        s.dc2pad[co * 256 + (y + 4) * 16 + (x + 4)] = gv;
+      }
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S7a: conv2 weight/bias gradient (sparse)
+    if (tid < 200) {
+      const int co = tid / 10, ci = tid % 10;
+      float acc[25];
+#pragma unroll
+      for (int k = 0; k < 25; ++k) acc[k] = 0.f;
+      for (int cell = 0; cell < 16; ++cell) {
+        const float gv = s.g2[co * 16 + cell];
+        if (gv != 0.f) {
+          const int arg = s.a2[co * 16 + cell];
+          const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
+          const float* src = &s.p1[ci * 144 + ay * 12 + ax];
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) acc[ky * 5 + kx] = fmaf(gv, src[ky * 12 + kx], acc[ky * 5 + kx]);
+        }
+      }
+      float* dst = &s.g[W2 + co * 250 + ci * 25];
+#pragma unroll
+      for (int k = 0; k < 25; ++k) dst[k] += acc[k];
+    } else if (tid < 220) {
+      const int co = tid - 200;
+      float d = 0.f;
+#pragma unroll
+      for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
+      s.g[B2 + co] += d;
+    }
+    // -------------------------------------------------------------- S7b: conv2 data gradient (dense, K split 3)
+    if (tid < 216) {
+      const int tile = tid % 36, half = (tid / 36) & 1, ks = tid / 72;
+      const int y0 = 2 * (tile / 6), x0 = 2 * (tile % 6);
+      const int co0 = ks * 7, co1 = ks == 2 ? 20 : co0 + 7;
+      float acc[4][5];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[p][c] = 0.f;
+      for (int co = co0; co < co1; ++co) {
+        if (s.m2[co] == 0.f) continue;            // channel dropped by Dropout2d: gradient plane is zero
+        float patch[6][6];
+        const float* src = &s.dc2pad[co * 256 + y0 * 16 + x0];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) patch[i][j] = src[i * 16 + j];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const float* wp = &s.w2b[((co * 25 + ky * 5 + kx) * 2 + half) * 8];
+            const float4 w = *reinterpret_cast<const float4*>(wp);
+            const float w4 = wp[4];
+            const float d00 = patch[4 - ky][4 - kx], d01 = patch[4 - ky][5 - kx];
+            const float d10 = patch[5 - ky][4 - kx], d11 = patch[5 - ky][5 - kx];
+            acc[0][0] = fmaf(w.x, d00, acc[0][0]); acc[0][1] = fmaf(w.y, d00, acc[0][1]);
+            acc[0][2] = fmaf(w.z, d00, acc[0][2]); acc[0][3] = fmaf(w.w, d00, acc[0][3]); acc[0][4] = fmaf(w4, d00, acc[0][4]);
+            acc[1][0] = fmaf(w.x, d01, acc[1][0]); acc[1][1] = fmaf(w.y, d01, acc[1][1]);
+            acc[1][2] = fmaf(w.z, d01, acc[1][2]); acc[1][3] = fmaf(w.w, d01, acc[1][3]); acc[1][4] = fmaf(w4, d01, acc[1][4]);
+            acc[2][0] = fmaf(w.x, d10, acc[2][0]); acc[2][1] = fmaf(w.y, d10, acc[2][1]);
+            acc[2][2] = fmaf(w.z, d10, acc[2][2]); acc[2][3] = fmaf(w.w, d10, acc[2][3]); acc[2][4] = fmaf(w4, d10, acc[2][4]);
+            acc[3][0] = fmaf(w.x, d11, acc[3][0]); acc[3][1] = fmaf(w.y, d11, acc[3][1]);
+            acc[3][2] = fmaf(w.z, d11, acc[3][2]); acc[3][3] = fmaf(w.w, d11, acc[3][3]); acc[3][4] = fmaf(w4, d11, acc[3][4]);
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        float* dst = &s.part[ks * 1440 + (half * 5 + c) * 144 + y0 * 12 + x0];
+        dst[0] = acc[0][c]; dst[1] = acc[1][c]; dst[12] = acc[2][c]; dst[13] = acc[3][c];
+      }
+    }
+    __syncthreads();
+
+    // -------------------------------------------------------------- S8a: through relu+pool of conv1
+    for (int o = tid; o < 1440; o += T)
+      s.g1[o] = s.p1[o] > 0.f ? (s.part[o] + s.part[1440 + o] + s.part[2880 + o]) : 0.f;
+    __syncthreads();
+
+    // -------------------------------------------------------------- S8b: conv1 weight/bias gradient (sparse)
+    if (tid < 250) {
+      const int c = tid / 25, k = tid % 25, ky = k / 5, kx = k % 5;
+      float acc = 0.f;
+      for (int cell = 0; cell < 144; ++cell) {
+        const float gv = s.g1[c * 144 + cell];
+        const int arg = s.a1[c * 144 + cell];
+        const int y = 2 * (cell / 12) + (arg >> 1) + ky, x = 2 * (cell % 12) + (arg & 1) + kx;
+        acc = fmaf(gv, s.x[y * 28 + x], acc);
+      }
+      s.g[W1 + tid] += acc;
+    } else if (tid - 250 < 6) {                   // 6 threads do the 10 bias sums (250..255)
+      for (int c = tid - 250; c < 10; c += 6) {
+        float d = 0.f;
+        for (int cell = 0; cell < 144; ++cell) d += s.g1[c * 144 + cell];
+        s.g[B1 + c] += d;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ flush
+  if (a.backward && blockIdx.x < a.B) {
+    for (int v = tid; v < NPAR / 4; v += T) {
+      const float4 q = *reinterpret_cast<const float4*>(&s.g[v * 4]);
+      red_add_v4(a.grads + v * 4, q.x, q.y, q.z, q.w);
+    }
+  }
+  if (tid == 0 && a.loss_acc != nullptr && blockIdx.x < a.B) {
+    atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
+    atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+  }
+}
+
+}  // namespace cn
+
+extern "C" {
+
+size_t b2_convnet_smem_bytes() { return sizeof(cn::Smem); }
+int b2_convnet_npar() { return cn::NPAR; }
+
+int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
+                           float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
+                           unsigned long long seed, long long sample_base, int B, int training, int backward,
+                           float inv_bsz, float p_drop, int max_ctas, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = sizeof(cn::Smem);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(cn::convnet_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cn::Args a;
+  a.params = params; a.grads = grads; a.x = x; a.target = target; a.loss_acc = loss_acc; a.out_logp = out_logp;
+  a.mask_out = mask_out; a.step = step; a.seed = seed; a.sample_base = sample_base; a.B = B; a.x_u8 = x_u8;
+  a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
+  a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f;
+  int grid = B;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) grid = 1;
+  cn::convnet_step_kernel<<<grid, cn::T, smem, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Fused  [peer-memory gradient all-reduce] + [1/world scale] + [momentum SGD]  for flat fp32 buffers.
+//
+// Replaces average_gradients() + optimizer.step() + optimizer.zero_grad() of the reference training
+// step (train_dist.py:118,123,124): 8 all-reduces + 8 divides + foreach-SGD + 8 memsets become ONE
+// kernel.  Every rank reads all peers' gradient buckets over NVSwitch (one-shot), sums them in fixed
+// rank order (bit-identical replicas), scales, applies  buf = mu*buf + g ; p -= lr*buf  (torch.optim.SGD
+// semantics with dampening 0, no nesterov, no weight decay -- train_dist.py:110), then -- after a second
+// flag barrier that proves every peer has finished reading -- zeroes its own bucket for the next step's
+// `red.add` accumulation and bumps the device-side step counter used by the dropout RNG.
+#include <cstdio>
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kSgdThreads = 512;
+
+struct SgdArgs {
+  PeerPtrs grads;            // symmetric flat fp32 gradient buckets (grads.p[rank] is ours)
+  SignalPads sig;
+  float* params;
+  float* momentum;
+  unsigned long long* step;  // incremented once per call (may be null)
+  size_t n_vec;              // float4 vectors
+  float lr, mu, scale;
+  int rank, world;
+  int zero_grads;
+};
+
+__global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
+  const int rank = a.rank, world = a.world;
+  uint32_t epoch = 0;
+  if (world > 1) {
+    epoch = barrier_epoch_load(a.sig, rank);
+    block_barrier_all_ranks(a.sig, rank, world, ++epoch);           // all gradient buckets are complete
+  }
+  const size_t stride = (size_t)gridDim.x * kSgdThreads;
+  // block-uniform trip count (barrier inside the loop)
+  for (size_t base = (size_t)blockIdx.x * kSgdThreads; base < a.n_vec; base += stride) {
+    const size_t v = base + threadIdx.x;
+    const bool ok = v < a.n_vec;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      uint4 raw[B2_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < B2_MAX_RANKS; ++r)
+        if (r < world) raw[r] = ld_cg_v4(reinterpret_cast<const uint4*>(a.grads.p[r]) + v);
+#pragma unroll
+      for (int r = 0; r < B2_MAX_RANKS; ++r)
+        if (r < world) {
+          g.x += __uint_as_float(raw[r].x); g.y += __uint_as_float(raw[r].y);
+          g.z += __uint_as_float(raw[r].z); g.w += __uint_as_float(raw[r].w);
+        }
+      g.x *= a.scale; g.y *= a.scale; g.z *= a.scale; g.w *= a.scale;
+      float4 m = reinterpret_cast<float4*>(a.momentum)[v];
+      float4 p = reinterpret_cast<float4*>(a.params)[v];
+      m.x = fmaf(a.mu, m.x, g.x); m.y = fmaf(a.mu, m.y, g.y); m.z = fmaf(a.mu, m.z, g.z); m.w = fmaf(a.mu, m.w, g.w);
+      p.x = fmaf(-a.lr, m.x, p.x); p.y = fmaf(-a.lr, m.y, p.y); p.z = fmaf(-a.lr, m.z, p.z); p.w = fmaf(-a.lr, m.w, p.w);
+      reinterpret_cast<float4*>(a.momentum)[v] = m;
+      reinterpret_cast<float4*>(a.params)[v] = p;
+    }
+    if (a.zero_grads) {
+      if (world > 1) block_barrier_all_ranks(a.sig, rank, world, ++epoch);   // peers are done reading this pass
+      if (ok) st_cg_v4(reinterpret_cast<uint4*>(a.grads.p[rank]) + v, make_uint4(0u, 0u, 0u, 0u));
+    }
+  }
+  if (world > 1 && threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
+  if (a.step != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.step += 1ull;
+}
+
+// Plain flat momentum SGD (generic models: gradients already averaged in `grad`)
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                       const float* __restrict__ g, size_t n, float lr, float mu,
+                                                       float wd, int zero_grad, float* gw) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  if (i < n4) {
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    gv.x = fmaf(wd, pv.x, gv.x); gv.y = fmaf(wd, pv.y, gv.y); gv.z = fmaf(wd, pv.z, gv.z); gv.w = fmaf(wd, pv.w, gv.w);
+    mv.x = fmaf(mu, mv.x, gv.x); mv.y = fmaf(mu, mv.y, gv.y); mv.z = fmaf(mu, mv.z, gv.z); mv.w = fmaf(mu, mv.w, gv.w);
+    pv.x = fmaf(-lr, mv.x, pv.x); pv.y = fmaf(-lr, mv.y, pv.y); pv.z = fmaf(-lr, mv.z, pv.z); pv.w = fmaf(-lr, mv.w, pv.w);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    if (zero_grad) reinterpret_cast<float4*>(gw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (i == 0) {
+    for (size_t t = n4 * 4; t < n; ++t) {      // tail (< 4 elements)
+      const float gt = fmaf(wd, p[t], g[t]);
+      m[t] = fmaf(mu, m[t], gt);
+      p[t] = fmaf(-lr, m[t], p[t]);
+      if (zero_grad) gw[t] = 0.f;
+    }
+  }
+}
+
+}  // namespace b2
+
+extern "C" {
+
+int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
+                            unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
+                            int world, int zero_grads, cudaStream_t stream) {
+  b2::SgdArgs a;
+  a.grads = *grads; a.sig = *sig; a.params = params; a.momentum = momentum; a.step = step;
+  a.n_vec = n_elems / 4; a.lr = lr; a.mu = mu; a.scale = scale; a.rank = rank; a.world = world;
+  a.zero_grads = zero_grads;
+  size_t blocks = (a.n_vec + b2::kSgdThreads - 1) / b2::kSgdThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;
+  b2::allreduce_sgd_kernel<<<(unsigned)blocks, b2::kSgdThreads, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
+                       cudaStream_t stream) {
+  const size_t n4 = (n / 4) > 0 ? n / 4 : 1;
+  const unsigned blocks = (unsigned)((n4 + 255) / 256);
+  b2::sgd_flat_kernel<<<blocks, 256, 0, stream>>>(p, m, g, n, lr, mu, wd, zero_grad, const_cast<float*>(g));
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

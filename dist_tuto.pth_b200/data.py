@@ -32,7 +32,7 @@ import torch
 from . import comm
 
 __all__ = ["Partition", "DataPartitioner", "partition_dataset", "SyntheticMNIST", "TensorImageDataset",
-           "BatchLoader", "load_mnist", "write_idx", "MNIST_MEAN", "MNIST_STD", "GLOBAL_BATCH"]
+           "BatchLoader", "NativeBatchLoader", "load_mnist", "write_idx", "MNIST_MEAN", "MNIST_STD", "GLOBAL_BATCH"]
 
 MNIST_MEAN, MNIST_STD = 0.1307, 0.3081   # train_dist.py:82
 GLOBAL_BATCH = 128                       # train_dist.py:85
@@ -279,6 +279,57 @@ class BatchLoader:
                 yield xs, ys
 
 
+class NativeBatchLoader:
+    """Same contract as :class:`BatchLoader`, served by the C++ prefetcher (csrc/loader.cpp).
+
+    A worker thread gathers + normalises the next batches into a ring of pinned
+    buffers while the GPU trains; the yielded tensors alias those buffers (the
+    fused trainer adopts them as CUDA-graph copy sources -> zero extra copies).
+    A buffer is recycled ``num_buffers - 1`` batches after it was yielded."""
+
+    def __init__(self, partition, batch_size: int, shuffle: bool = True, drop_last: bool = False,
+                 pin_memory: Optional[bool] = None, seed: Optional[int] = None, raw_uint8: bool = False,
+                 num_buffers: int = 6):
+        from .ops import _ext
+        base = partition.data if isinstance(partition, Partition) else partition
+        if not hasattr(base, "images"):
+            raise TypeError("NativeBatchLoader needs a tensor-backed dataset (TensorImageDataset)")
+        self.dataset = partition
+        self.batch_size = int(batch_size)
+        idx = partition.index_tensor() if isinstance(partition, Partition) else torch.arange(len(partition))
+        pin = torch.cuda.is_available() if pin_memory is None else pin_memory
+        seed = int(torch.initial_seed()) & 0x7FFFFFFF if seed is None else seed
+        self.num_buffers = max(3, num_buffers)
+        self._l = _ext.C().NativeLoader(base.images, base.labels, idx, self.batch_size, self.num_buffers, shuffle,
+                                        drop_last, raw_uint8, base.mean, base.std, seed, pin)
+        self._epoch = 0
+        self.before_recycle = None     # optional callable: make sure the oldest yielded batch was consumed
+
+    def __len__(self) -> int:
+        return int(self._l.num_batches())
+
+    def __iter__(self):
+        self._l.start_epoch(self._epoch)
+        self._epoch += 1
+        out = 0
+        try:
+            while True:
+                if out >= self.num_buffers - 1:
+                    if self.before_recycle is not None:
+                        self.before_recycle()
+                    self._l.release()
+                    out -= 1
+                r = self._l.next()
+                if r is None:
+                    break
+                out += 1
+                yield r
+        finally:
+            if self.before_recycle is not None:
+                self.before_recycle()
+            self._l.stop()
+
+
 _DATASET_CACHE = {}
 
 
@@ -293,7 +344,8 @@ def default_dataset(root: str = "./data", n: int = 60000, seed: int = 1234) -> T
 
 
 def partition_dataset(dataset=None, global_batch: int = GLOBAL_BATCH, seed: int = 1234,
-                      rank: Optional[int] = None, world_size: Optional[int] = None, **loader_kw):
+                      rank: Optional[int] = None, world_size: Optional[int] = None, native: Optional[bool] = None,
+                      **loader_kw):
     """Shard the training set for this rank; returns ``(loader, bsz)``.
 
     Same contract as train_dist.py:74-91: equal shards ``[1/size] * size``,
@@ -308,4 +360,8 @@ def partition_dataset(dataset=None, global_batch: int = GLOBAL_BATCH, seed: int 
         raise ValueError(f"world size {size} exceeds the global batch {global_batch}")
     sizes = [1.0 / size for _ in range(size)]
     part = DataPartitioner(dataset, sizes, seed=seed).use(rank)
+    if native is None:
+        native = hasattr(dataset, "images") and torch.cuda.is_available()
+    if native:
+        return NativeBatchLoader(part, batch_size=bsz, shuffle=True, **loader_kw), bsz
     return BatchLoader(part, batch_size=bsz, shuffle=True, **loader_kw), bsz

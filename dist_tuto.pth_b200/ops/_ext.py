@@ -1,0 +1,57 @@
+"""Loader for the in-tree native extension ``dist_tuto.pth_b200/_C.so``.
+
+The extension is built by ``build.py`` (nvcc, sm_100a only) and lives in the
+package directory so it travels with the repo snapshot.  There is NO silent
+PyTorch fallback for the ops it provides: if it cannot be loaded, ``C()`` raises
+with the build instruction."""
+from __future__ import annotations
+
+import importlib.util
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_PKG, "_C.so")
+_mod = None
+_err = None
+_lock = threading.Lock()
+
+
+def so_path() -> str:
+    return _SO
+
+
+def available() -> bool:
+    try:
+        C()
+        return True
+    except Exception:
+        return False
+
+
+def C():
+    """Return the loaded extension module (loads it on first use)."""
+    global _mod, _err
+    if _mod is not None:
+        return _mod
+    with _lock:
+        if _mod is not None:
+            return _mod
+        if not os.path.isfile(_SO):
+            if os.environ.get("B200DIST_AUTOBUILD", "0") == "1":
+                from .. import build as _b
+                _b.build(verbose=False)
+            else:
+                raise ImportError(f"native extension missing: {_SO}\n"
+                                  "build it with:  python -c 'import __graft_entry__ as g; g.build()'  "
+                                  "(or set B200DIST_AUTOBUILD=1)")
+        import torch  # noqa: F401  (libtorch must be loaded first)
+        spec = importlib.util.spec_from_file_location("dist_tuto.pth_b200._C", _SO)
+        mod = importlib.util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(mod)
+        except Exception as e:  # pragma: no cover
+            _err = e
+            raise ImportError(f"failed to load {_SO}: {e}") from e
+        _mod = mod
+        return _mod

@@ -1,0 +1,305 @@
+"""Fused sm_100a training engine for the tutorial ConvNet.
+
+One training step of the reference (train_dist.py:118-124:
+``zero_grad -> model(data) -> nll_loss -> backward -> average_gradients -> step``)
+is TWO kernels here, replayed as one CUDA graph:
+
+  1. ``convnet_step``   (csrc/convnet.cu)  forward + loss + backward, one CTA per
+     sample, gradients ``red.add``-ed into a flat fp32 bucket that lives in
+     symmetric peer memory;
+  2. ``allreduce_sgd``  (csrc/sgd.cu)      every rank reads all peers' buckets over
+     NVSwitch, averages, applies momentum SGD to the flat fp32 parameters,
+     re-zeroes its bucket and bumps the RNG step counter.
+
+The graph also contains the H2D copy of the batch from a pinned staging slot
+and the D2H copy of the running loss, so the host issues ONE launch per step.
+
+Parameter names/shapes/order follow the reference ``Net`` (state_dicts
+interchange with ``models.convnet.Net``).
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import comm
+from ..models.convnet import PARAM_SHAPES, Net
+from . import _ext
+
+__all__ = ["LAYOUT", "NPAR", "pack_params", "unpack_params", "convnet_loss_and_grads", "convnet_forward",
+           "FusedTrainer"]
+
+# padded flat layout: must match csrc/convnet.cu
+LAYOUT: Dict[str, int] = {"conv1.weight": 0, "conv1.bias": 252, "conv2.weight": 264, "conv2.bias": 5264,
+                          "fc1.weight": 5284, "fc1.bias": 21284, "fc2.weight": 21336, "fc2.bias": 21836}
+NPAR = 21848
+NPAR_ALLOC = 21888          # multiple of 64 elements (two-shot / NVLS slicing for any world <= 8)
+
+
+def unpack_params(flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Named views (reference parameter names) into a flat buffer."""
+    out = {}
+    for name, shape in PARAM_SHAPES:
+        n = 1
+        for s in shape:
+            n *= s
+        out[name] = flat[LAYOUT[name]:LAYOUT[name] + n].view(shape)
+    return out
+
+
+def pack_params(src, device=None) -> torch.Tensor:
+    """Flat fp32 buffer from a ``Net`` / state_dict (padding zero)."""
+    sd = src.state_dict() if hasattr(src, "state_dict") else src
+    dev = device if device is not None else next(iter(sd.values())).device
+    flat = torch.zeros(NPAR_ALLOC, dtype=torch.float32, device=dev)
+    views = unpack_params(flat)
+    for name, _ in PARAM_SHAPES:
+        views[name].copy_(sd[name].detach().to(torch.float32))
+    return flat
+
+
+def convnet_loss_and_grads(params: torch.Tensor, x: torch.Tensor, target: torch.Tensor, training: bool = False,
+                           seed: int = 0, step: Optional[torch.Tensor] = None, sample_base: int = 0,
+                           p_drop: float = 0.5, return_masks: bool = False, grads: Optional[torch.Tensor] = None):
+    """Functional entry: returns ``(mean_nll, grads_flat[, masks])`` for one batch (used by tests)."""
+    C = _ext.C()
+    B = target.numel()
+    if grads is None:
+        grads = torch.zeros(NPAR_ALLOC, dtype=torch.float32, device=params.device)
+    acc = torch.zeros(2, dtype=torch.float32, device=params.device)
+    masks = torch.empty(B, 70, dtype=torch.float32, device=params.device) if return_masks else None
+    C.convnet_step(params, grads, x.contiguous(), target.contiguous(), acc, None, masks, step, seed, sample_base,
+                   training, 1.0 / B, p_drop, 0)
+    return (acc[0], grads, masks) if return_masks else (acc[0], grads)
+
+
+def convnet_forward(params: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Eval-mode forward: log-probabilities ``[B,10]`` (same semantics as ``Net.eval()(x)``)."""
+    C = _ext.C()
+    B = x.shape[0]
+    out = torch.empty(B, 10, dtype=torch.float32, device=params.device)
+    dummy_t = torch.zeros(B, dtype=torch.int64, device=params.device)
+    C.convnet_step(params, None, x.contiguous(), dummy_t, None, out, None, None, 0, 0, False, 1.0 / max(B, 1), 0.5, 0)
+    return out
+
+
+class _Slot:
+    __slots__ = ("x_pin", "y_pin", "loss_pin", "graph", "event", "busy")
+
+
+class FusedTrainer:
+    """Synchronous data-parallel SGD for the ConvNet, fully fused (see module docstring)."""
+
+    def __init__(self, bsz: int, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234, device=None,
+                 p_drop: float = 0.5, group=None, raw_uint8: bool = False, num_slots: int = 4,
+                 use_graph: bool = True, init_from: Optional[Net] = None):
+        self.C = _ext.C()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.bsz, self.lr, self.mu, self.seed, self.p_drop = int(bsz), float(lr), float(momentum), int(seed), p_drop
+        self.group = group
+        self.world = comm.get_world_size(group)
+        self.rank = comm.group_ranks(group).index(comm.get_rank()) if comm.is_initialized() else 0
+        self.raw_uint8 = raw_uint8
+        self.training = True
+        # identical replicas: same seed AND an explicit broadcast (the reference relies on the seed only)
+        if init_from is None:
+            torch.manual_seed(seed)
+            init_from = Net(p_drop)
+        self.params = pack_params(init_from, self.device)
+        if self.world > 1:
+            dist.broadcast(self.params, src=comm.group_ranks(group)[0], group=comm._g(group))
+        self.momentum = torch.zeros_like(self.params)
+        self.symm = None
+        self.grad_handle = None
+        if self.world > 1:
+            from ..parallel import symm
+            self.symm = symm.lookup_world(comm._g(group)) or symm.init_world(comm._g(group))
+            self.grad_handle = self.symm.alloc(NPAR_ALLOC, torch.float32)
+            self.grads = self.grad_handle.local
+            self._grad_ptrs, self._sig_ptrs = self.grad_handle.ptrs, self.grad_handle.sig_ptrs
+        else:
+            self.grads = torch.zeros(NPAR_ALLOC, dtype=torch.float32, device=self.device)
+            self._grad_ptrs, self._sig_ptrs = [self.grads.data_ptr()], [0]
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.loss_acc = torch.zeros(2, dtype=torch.float32, device=self.device)   # [sum of batch-mean nll, #correct]
+        xdt = torch.uint8 if raw_uint8 else torch.float32
+        self.x_dev = torch.zeros(self.bsz, 1, 28, 28, dtype=xdt, device=self.device)
+        self.y_dev = torch.zeros(self.bsz, dtype=torch.int64, device=self.device)
+        self.use_graph = use_graph
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = []
+        for _ in range(max(2, num_slots)):
+            s = _Slot()
+            s.x_pin = torch.zeros(self.bsz, 1, 28, 28, dtype=xdt).pin_memory()
+            s.y_pin = torch.zeros(self.bsz, dtype=torch.int64).pin_memory()
+            s.loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+            s.graph, s.event, s.busy = None, torch.cuda.Event(), False
+            self.slots.append(s)
+        self._ext_slots: Dict[int, _Slot] = {}      # loader-owned pinned buffers -> their graphs
+        self._order = deque()                       # slots in flight, oldest first
+        self._nstep = 0
+        self._loss_read = 0.0                       # cumulative loss already returned by pop_loss_sum
+        self._last_loss_cum = 0.0
+        self.gpu_launches_per_step = 2              # convnet_step + allreduce_sgd (our kernels)
+        self._warm()
+
+    # ------------------------------------------------------------------ kernels
+    def _kernels(self, x, y, B):
+        self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
+                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0)
+        self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
+                             self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True)
+
+    def _warm(self):
+        # forward-only launch: sets the kernel's dynamic-smem attribute outside of graph capture
+        with torch.cuda.stream(self.stream):
+            self.C.convnet_step(self.params, None, self.x_dev, self.y_dev, None, None, None, None, 0, 0, False,
+                                1.0 / self.bsz, self.p_drop, 0)
+        self.stream.synchronize()
+
+    def _capture(self, slot: _Slot):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            self.x_dev.copy_(slot.x_pin, non_blocking=True)
+            self.y_dev.copy_(slot.y_pin, non_blocking=True)
+            self._kernels(self.x_dev, self.y_dev, self.bsz)
+            slot.loss_pin.copy_(self.loss_acc, non_blocking=True)
+        slot.graph = g
+
+    # ------------------------------------------------------------------ stepping
+    def _retire_oldest(self):
+        s = self._order.popleft()
+        s.event.synchronize()
+        s.busy = False
+        self._last_loss_cum = float(s.loss_pin[0])
+        return s
+
+    def sync_lag(self, keep: int = 0):
+        """Block until at most ``keep`` steps are still in flight (bounds host run-ahead)."""
+        while len(self._order) > keep:
+            self._retire_oldest()
+
+    def _slot_for(self, data: torch.Tensor, target: torch.Tensor) -> _Slot:
+        key = data.data_ptr()
+        s = self._ext_slots.get(key)
+        if s is not None:
+            return s
+        if data.device.type == "cpu" and data.is_pinned() and target.is_pinned() and \
+                data.dtype == self.x_dev.dtype and data.numel() == self.x_dev.numel() and len(self._ext_slots) < 16:
+            # a loader-owned pinned buffer: adopt it as a graph source (zero extra host copies)
+            s = _Slot()
+            s.x_pin, s.y_pin = data.view(self.bsz, 1, 28, 28), target
+            s.loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+            s.graph, s.event, s.busy = None, torch.cuda.Event(), False
+            self._ext_slots[key] = s
+            return s
+        # generic tensor: stage through one of our own pinned slots
+        s = self.slots[self._nstep % len(self.slots)]
+        if s.busy:
+            while s.busy:
+                self._retire_oldest()
+        if data.device.type == "cpu":
+            s.x_pin.copy_(data.view_as(s.x_pin))
+            s.y_pin.copy_(target)
+        return s
+
+    def step(self, data: torch.Tensor, target: torch.Tensor) -> None:
+        """One synchronous-SGD step on this rank's mini-batch (async; see ``sync_lag``)."""
+        B = target.numel()
+        if B != self.bsz or not self.use_graph or data.is_cuda:
+            self._eager_step(data, target, B)
+            return
+        s = self._slot_for(data, target)
+        if s.busy:
+            while s.busy:
+                self._retire_oldest()
+        if s.graph is None:
+            self.sync_lag(0)
+            self._capture(s)
+        with torch.cuda.stream(self.stream):
+            s.graph.replay()
+            s.event.record(self.stream)
+        s.busy = True
+        self._order.append(s)
+        self._nstep += 1
+        if len(self._order) > len(self.slots) - 2:
+            self._retire_oldest()
+
+    def _eager_step(self, data, target, B):
+        self.sync_lag(0)
+        with torch.cuda.stream(self.stream):
+            x = data.to(self.device, non_blocking=True).contiguous()
+            y = target.to(self.device, non_blocking=True).contiguous()
+            if (x.dtype == torch.uint8) != self.raw_uint8 and x.dtype != torch.uint8:
+                x = x.to(torch.float32)
+            self._kernels(x, y, B)
+        self.stream.synchronize()
+        self._last_loss_cum = float(self.loss_acc[0].item())
+        self._nstep += 1
+
+    def pop_loss_sum(self) -> float:
+        """Sum of per-batch mean losses since the previous call (one sync)."""
+        self.sync_lag(0)
+        self.stream.synchronize()
+        cum = float(self.loss_acc[0].item())
+        out = cum - self._loss_read
+        self._loss_read = cum
+        return out
+
+    def last_loss_cumulative(self) -> float:
+        """Cumulative loss as of the most recently *retired* step (read from the pinned D2H copy)."""
+        return self._last_loss_cum
+
+    # ------------------------------------------------------------------ nn.Module-like surface
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self.sync_lag(0)
+            self.training = mode
+            for s in list(self.slots) + list(self._ext_slots.values()):
+                s.graph = None          # dropout on/off is baked into the captured launch
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def parameters(self):
+        return list(unpack_params(self.params).values())
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        self.sync_lag(0)
+        self.stream.synchronize()
+        x = x.to(self.device)
+        if x.dtype != torch.uint8:
+            x = x.to(torch.float32)
+        return convnet_forward(self.params, x)
+
+    def state_dict(self):
+        self.sync_lag(0)
+        self.stream.synchronize()
+        p, m = unpack_params(self.params), unpack_params(self.momentum)
+        return {"model": {k: v.detach().cpu().clone() for k, v in p.items()},
+                "momentum": {k: v.detach().cpu().clone() for k, v in m.items()},
+                "steps": int(self.step_counter.item()), "lr": self.lr, "mu": self.mu}
+
+    def load_state_dict(self, sd):
+        self.sync_lag(0)
+        model = sd.get("model", sd)
+        views = unpack_params(self.params)
+        for k, v in model.items():
+            views[k].copy_(v)
+        if "momentum" in sd:
+            mv = unpack_params(self.momentum)
+            for k, v in sd["momentum"].items():
+                mv[k].copy_(v)
+        if "steps" in sd:
+            self.step_counter.fill_(int(sd["steps"]))
+        torch.cuda.synchronize(self.device)
+
+    def to_module(self) -> Net:
+        """A torch ``Net`` holding copies of the current parameters."""
+        net = Net(self.p_drop)
+        net.load_state_dict(self.state_dict()["model"])
+        return net

@@ -1,0 +1,190 @@
+"""Workers for the GPU-multi tier (spawned, one process per GPU, backend 'b200')."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+import dist_tuto.pth_b200 as b2
+from dist_tuto.pth_b200 import ring
+from dist_tuto.pth_b200.parallel import symm
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def w_symm_allreduce(rank, size):
+    dev = _dev()
+    w = symm.lookup_world(None)
+    assert w is not None and w.world == size
+    info = w.describe()
+    if rank == 0:
+        print("SYMM", info, flush=True)
+    variants = [0, 1] + ([2] if w.multicast else [])
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        for n in (1, 7, 64, 1000, 21888, 65536 + 3, 1 << 20):
+            g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+            local = torch.randn(n, generator=g).to(dev).to(dtype)
+            ref = local.clone().float()
+            dist.all_reduce(ref)                      # NCCL oracle (fp32 accumulate)
+            ref = ref / size
+            # (a) zero-copy symmetric buffer, every variant
+            hd = w.alloc(n, dtype)
+            for v in variants:
+                hd.local.zero_()
+                hd.local[:n].copy_(local)
+                torch.cuda.synchronize()
+                dist.barrier()
+                w.all_reduce_(hd.local, scale=1.0 / size, handle=hd, variant=v)
+                torch.cuda.synchronize()
+                got = hd.local[:n].float()
+                assert torch.allclose(got, ref, atol=tol, rtol=tol), (str(dtype), n, v, float((got - ref).abs().max()))
+                # bit-identical on every rank (fixed reduction order)
+                mine = hd.local[:n].clone()
+                other = mine.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(mine, other), ("replica mismatch", str(dtype), n, v)
+            # (b) arbitrary tensor through the staging buffer (fused copy-in/out or ragged path)
+            for v in variants:
+                t = local.clone()
+                w.all_reduce_(t, scale=1.0 / size, variant=v)
+                torch.cuda.synchronize()
+                assert torch.allclose(t.float(), ref, atol=tol, rtol=tol), ("staged", str(dtype), n, v)
+    # (c) fp32 tensor, bf16 on the wire
+    t = torch.randn(4096, generator=torch.Generator().manual_seed(5 + rank)).to(dev)
+    ref = t.clone()
+    dist.all_reduce(ref)
+    w.all_reduce_(t, wire=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.allclose(t, ref, atol=5e-2, rtol=5e-2)
+    # (d) repeated calls: flag reuse must not race
+    hd = w.alloc(4096, torch.float32)
+    for it in range(200):
+        hd.local.fill_(float(rank + it))
+        w.all_reduce_(hd.local, handle=hd, variant=it % len(variants))
+    torch.cuda.synchronize()
+    expect = float(sum(r + 199 for r in range(size)))
+    assert torch.allclose(hd.local, torch.full_like(hd.local, expect)), float(hd.local[0])
+    # (e) public API routes CUDA float SUM to the fused kernels
+    t = torch.ones(10, device=dev)
+    b2.all_reduce(t)
+    assert float(t[0]) == size
+    dist.barrier()
+
+
+def w_average_gradients_gpu(rank, size):
+    dev = _dev()
+    torch.manual_seed(1234)
+    model = b2.Net().to(dev).eval()
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn(8, 1, 28, 28, generator=g).to(dev)
+    y = torch.randint(0, 10, (8,), generator=g).to(dev)
+    F.nll_loss(model(x), y).backward()
+    local = [p.grad.clone() for p in model.parameters()]
+    ref = []
+    for gl in local:
+        r = gl.clone()
+        dist.all_reduce(r)
+        ref.append(r / size)
+    b2.average_gradients(model)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.allclose(p.grad, r, atol=1e-6)
+    # overlapped bucketed DDP on symmetric buckets
+    from dist_tuto.pth_b200.parallel.ddp import DistributedDataParallel
+    torch.manual_seed(7 + rank)
+    m2 = b2.Net().to(dev).eval()
+    ddp = DistributedDataParallel(m2, bucket_cap_bytes=16 << 10)
+    assert len(ddp.buckets) >= 2 and ddp.buckets[0].world is not None
+    m3 = b2.Net().to(dev).eval()
+    m3.load_state_dict(m2.state_dict())
+    F.nll_loss(m3(x), y).backward()
+    ref = []
+    for p in m3.parameters():
+        r = p.grad.clone()
+        dist.all_reduce(r)
+        ref.append(r / size)
+    for it in range(3):
+        ddp.zero_grad()
+        F.nll_loss(ddp(x), y).backward()
+        b2.average_gradients(m2)
+        torch.cuda.synchronize()
+        for p, r in zip(m2.parameters(), ref):
+            assert torch.allclose(p.grad, r, atol=1e-6), it
+    dist.barrier()
+
+
+def w_fused_trainer(rank, size):
+    """World-N fused trainer == single-process torch SGD on the concatenated global batch."""
+    dev = _dev()
+    from dist_tuto.pth_b200.models.convnet import Net
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer, unpack_params
+    bsz = 16
+    torch.manual_seed(21)
+    ref = Net(p_drop=0.0).to(dev)
+    tr = FusedTrainer(bsz, lr=0.05, momentum=0.5, seed=21, device=dev, p_drop=0.0, init_from=ref)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.5)
+    for i in range(5):
+        g = torch.Generator().manual_seed(300 + i)
+        xg = torch.randn(bsz * size, 1, 28, 28, generator=g)
+        yg = torch.randint(0, 10, (bsz * size,), generator=g)
+        xs, ys = xg[rank * bsz:(rank + 1) * bsz].contiguous().pin_memory(), yg[rank * bsz:(rank + 1) * bsz].contiguous().pin_memory()
+        tr.step(xs, ys)
+        opt.zero_grad()
+        F.nll_loss(ref(xg.to(dev)), yg.to(dev)).backward()     # mean over the GLOBAL batch
+        opt.step()
+    tr.sync_lag(0)
+    torch.cuda.synchronize()
+    views = unpack_params(tr.params)
+    for name, p in ref.named_parameters():
+        assert torch.allclose(views[name], p.detach(), atol=3e-4, rtol=2e-3), name
+    # replicas bit-identical
+    mine = tr.params.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other)
+    # with dropout on: still bit-identical replicas, finite loss
+    tr2 = FusedTrainer(bsz, seed=5, device=dev, p_drop=0.5)
+    for i in range(20):
+        g = torch.Generator().manual_seed(900 + i * size + rank)
+        tr2.step(torch.randn(bsz, 1, 28, 28, generator=g).pin_memory(), torch.randint(0, 10, (bsz,), generator=g).pin_memory())
+    loss = tr2.pop_loss_sum()
+    assert loss == loss and loss > 0
+    mine = tr2.params.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other)
+    dist.barrier()
+
+
+def w_p2p_ring_gpu(rank, size):
+    dev = _dev()
+    t = torch.zeros(4, device=dev)
+    if rank == 0:
+        t += 1
+        b2.send(t, dst=1)
+    elif rank == 1:
+        b2.recv(t, src=0)
+        assert float(t[0]) == 1.0
+    send = torch.arange(6, dtype=torch.float32, device=dev) * (rank + 1)
+    recv = torch.zeros(6, device=dev)
+    b2.allreduce(send, recv)
+    torch.cuda.synchronize()
+    assert torch.allclose(recv, torch.arange(6, dtype=torch.float32, device=dev) * sum(r + 1 for r in range(size)))
+    recv2 = torch.zeros(1000, device=dev)
+    src = torch.randn(1000, generator=torch.Generator().manual_seed(rank)).to(dev)
+    ring.allreduce_chunked(src, recv2)
+    ref = src.clone()
+    dist.all_reduce(ref)
+    assert torch.allclose(recv2, ref, atol=1e-4)
+    dist.barrier()
+
+
+def w_train_fused_e2e(rank, size):
+    from dist_tuto.pth_b200.data import SyntheticMNIST
+    ds = SyntheticMNIST(n=2048, seed=5)
+    logs = []
+    cfg = b2.TrainConfig(epochs=3, dataset=ds, lr=0.1, log=lambda *a: logs.append(a))
+    out = b2.train(rank, size, cfg)
+    assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
+    dist.barrier()

@@ -1,0 +1,185 @@
+"""GPU-single tier: every sm_100a kernel against a plain PyTorch fp32 oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda", 0)
+
+
+def _net(dev, seed=0):
+    from dist_tuto.pth_b200.models.convnet import Net
+    torch.manual_seed(seed)
+    return Net().to(dev)
+
+
+def _batch(dev, B, seed=1):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, 1, 28, 28, generator=g).to(dev)
+    y = torch.randint(0, 10, (B,), generator=g).to(dev)
+    return x, y
+
+
+def _masked_forward(net, x, m2, mh):
+    """Oracle forward with explicit dropout scales (m2: [B,20] channel scales, mh: [B,50])."""
+    h = F.relu(F.max_pool2d(net.conv1(x), 2))
+    h = net.conv2(h) * m2[:, :, None, None]
+    h = F.relu(F.max_pool2d(h, 2)).reshape(-1, 320)
+    h = F.relu(net.fc1(h)) * mh
+    return F.log_softmax(net.fc2(h), dim=1)
+
+
+def test_extension_is_loaded_not_a_fallback():
+    from dist_tuto.pth_b200.ops import _ext
+    C = _ext.C()
+    assert C.convnet_npar() == 21848 and C.gemm_available()
+
+
+@pytest.mark.parametrize("B", [1, 7, 128, 300])
+def test_convnet_forward_matches_torch(dev, B):
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_forward, pack_params
+    net = _net(dev).eval()
+    x, _ = _batch(dev, B)
+    out = convnet_forward(pack_params(net), x)
+    ref = net(x)
+    assert out.shape == (B, 10)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("B", [1, 16, 128, 200])
+def test_convnet_loss_and_grads_match_autograd(dev, B):
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, pack_params, unpack_params
+    net = _net(dev, seed=3).eval()                       # eval: dropout off, autograd still on
+    x, y = _batch(dev, B, seed=5)
+    loss, grads = convnet_loss_and_grads(pack_params(net), x, y, training=False)
+    ref_loss = F.nll_loss(net(x), y)
+    ref_loss.backward()
+    assert torch.allclose(loss, ref_loss, atol=1e-4, rtol=1e-4)
+    views = unpack_params(grads)
+    for name, p in net.named_parameters():
+        scale = p.grad.abs().max().clamp_min(1e-6)
+        err = (views[name] - p.grad).abs().max() / scale
+        assert err < 2e-3, (name, float(err))
+    # padding between tensors stays zero
+    assert float(grads[250:252].abs().sum()) == 0.0
+
+
+def test_convnet_training_dropout_matches_masked_oracle(dev):
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, pack_params, unpack_params
+    net = _net(dev, seed=4).eval()
+    B = 64
+    x, y = _batch(dev, B, seed=6)
+    step = torch.tensor([3], dtype=torch.int64, device=dev)
+    loss, grads, masks = convnet_loss_and_grads(pack_params(net), x, y, training=True, seed=77, step=step,
+                                                return_masks=True)
+    vals = set(masks.unique().tolist())
+    assert vals <= {0.0, 2.0} and len(vals) == 2          # p=0.5 -> scale 2 or dropped
+    assert 0.3 < float((masks > 0).float().mean()) < 0.7
+    ref_loss = F.nll_loss(_masked_forward(net, x, masks[:, :20], masks[:, 20:]), y)
+    ref_loss.backward()
+    assert torch.allclose(loss, ref_loss, atol=1e-4, rtol=1e-4)
+    views = unpack_params(grads)
+    for name, p in net.named_parameters():
+        scale = p.grad.abs().max().clamp_min(1e-6)
+        assert (views[name] - p.grad).abs().max() / scale < 2e-3, name
+    # different step -> different masks; same step -> same masks
+    _, _, m_same = convnet_loss_and_grads(pack_params(net), x, y, training=True, seed=77, step=step, return_masks=True)
+    _, _, m_diff = convnet_loss_and_grads(pack_params(net), x, y, training=True, seed=77, step=step + 1,
+                                          return_masks=True)
+    assert torch.equal(masks, m_same) and not torch.equal(masks, m_diff)
+
+
+def test_convnet_uint8_input_normalised_in_kernel(dev):
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_forward, pack_params
+    net = _net(dev).eval()
+    xu = torch.randint(0, 256, (32, 1, 28, 28), dtype=torch.uint8, device=dev)
+    xf = (xu.float() / 255.0 - 0.1307) / 0.3081
+    assert torch.allclose(convnet_forward(pack_params(net), xu), net(xf), atol=3e-4, rtol=1e-4)
+
+
+def test_sgd_flat_matches_torch(dev):
+    from dist_tuto.pth_b200.ops import _ext
+    C = _ext.C()
+    n = 10007
+    p = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev)
+    m = torch.zeros(n, device=dev)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([ref], lr=0.01, momentum=0.5)
+    for _ in range(3):
+        ref.grad = g.clone()
+        opt.step()
+        C.sgd_flat(p, m, g, 0.01, 0.5, 0.0, False)
+    assert torch.allclose(p, ref.detach(), atol=1e-6)
+
+
+def test_fused_trainer_matches_torch_sgd_single_gpu(dev):
+    from dist_tuto.pth_b200.models.convnet import Net
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer, unpack_params
+    torch.manual_seed(11)
+    ref = Net(p_drop=0.0).to(dev)
+    tr = FusedTrainer(32, lr=0.05, momentum=0.5, seed=11, device=dev, p_drop=0.0, init_from=ref)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.5)
+    losses = []
+    for i in range(6):
+        x, y = _batch(dev, 32, seed=100 + i)
+        xp, yp = x.cpu().pin_memory(), y.cpu().pin_memory()
+        tr.step(xp, yp)                                  # graph path, pinned host input
+        opt.zero_grad()
+        loss = F.nll_loss(ref(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    got = tr.pop_loss_sum()
+    assert abs(got - sum(losses)) < 1e-3 * max(1.0, abs(sum(losses)))
+    views = unpack_params(tr.params)
+    for name, p in ref.named_parameters():
+        assert torch.allclose(views[name], p.detach(), atol=2e-4, rtol=1e-3), name
+    sd = tr.state_dict()
+    assert sd["steps"] == 6 and set(sd["model"]) == {n for n, _ in ref.named_parameters()}
+    # eval forward through the trainer == torch module with the same weights
+    x, _ = _batch(dev, 8, seed=999)
+    assert torch.allclose(tr.eval()(x), tr.to_module().to(dev).eval()(x), atol=2e-4)
+
+
+def test_fused_trainer_short_batch_and_device_input(dev):
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    tr = FusedTrainer(16, seed=1, device=dev, p_drop=0.5)
+    x, y = _batch(dev, 5)
+    tr.step(x, y)                                        # eager path: short batch, device tensors
+    assert tr.pop_loss_sum() > 0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 50, 320), (1000, 10, 512), (300, 200, 136), (64, 32, 8),
+                                   (4096, 512, 1024)])
+def test_tcgen05_gemm_matches_torch(dev, M, N, K):
+    from dist_tuto.pth_b200.ops.gemm import linear_bf16
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = a.float() @ w.float().t() + bias
+    out = linear_bf16(a, w, bias, relu=False, out_dtype=torch.float32)
+    assert out.shape == (M, N)
+    assert torch.allclose(out, ref, atol=2e-2, rtol=2e-2), float((out - ref).abs().max())
+    out_r = linear_bf16(a, w, bias, relu=True, out_dtype=torch.bfloat16)
+    assert torch.allclose(out_r.float(), ref.relu(), atol=6e-2, rtol=3e-2)
+
+
+def test_train_loop_single_gpu_fused(dev):
+    import dist_tuto.pth_b200 as b2
+    from dist_tuto.pth_b200.data import SyntheticMNIST
+    ds = SyntheticMNIST(n=2048, seed=5)
+    out = {}
+
+    def fn(rank, size):
+        out.update(b2.train(rank, size, b2.TrainConfig(epochs=3, dataset=ds, lr=0.1, log=lambda *a: None)))
+
+    b2.init_processes(0, 1, fn, backend="b200", master_port=b2.find_free_port())
+    assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
