@@ -1,0 +1,120 @@
+"""All-reduce bus bandwidth sweep (BASELINE.json config #4): fused peer-memory variants vs NCCL.
+
+    python bench/allreduce_sweep.py --gpus N [--max-mb 1024] [--out gpurun_out/sweep_N.json]
+
+For every size 1 KB .. max: one-shot / two-shot / NVLS (when exposed) on a symmetric fp32 buffer (in place,
+1/N scale fused) and ``dist.all_reduce`` (NCCL) + ``div_`` (what the reference's average_gradients does per
+tensor).  Timed with CUDA events on the launching stream after warm-up, MAX over ranks;
+busBW = 2(N-1)/N * bytes / t, reported against the measured 770 GB/s peer-copy figure (900 nominal).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dist_tuto.pth_b200 as b2  # noqa: E402
+from dist_tuto.pth_b200.parallel import symm  # noqa: E402
+
+ARGS = None
+
+
+def tmax(ms, dev):
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_op(fn, iters, dev):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return tmax(e0.elapsed_time(e1) / iters, dev)
+
+
+def body(rank, size):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    w = symm.lookup_world(None)
+    max_bytes = ARGS.max_mb << 20
+    sizes = []
+    s = 1024
+    while s <= max_bytes:
+        sizes.append(s)
+        s *= 4 if s >= (1 << 20) else 2
+    if sizes[-1] != max_bytes:
+        sizes.append(max_bytes)
+    hd = w.alloc(max_bytes // 4, torch.float32)
+    rows = []
+    variants = [("oneshot", 0), ("twoshot", 1)] + ([("nvls", 2)] if w.multicast else [])
+    for nbytes in sizes:
+        n = nbytes // 4
+        t = hd.local[:n]
+        plain = torch.ones(n, device=dev)
+        iters = 200 if nbytes <= (1 << 20) else (40 if nbytes <= (64 << 20) else 10)
+        row = {"bytes": nbytes}
+        for name, v in variants:
+            if v == 0 and nbytes > (8 << 20):
+                continue
+            t.fill_(1.0)
+            ms = time_op(lambda: w.all_reduce_(t, scale=1.0 / size, handle=hd, variant=v), iters, dev)
+            row[name + "_us"] = ms * 1e3
+            row[name + "_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
+            assert abs(float(t[0]) - 1.0) < 1e-3, (name, float(t[0]))
+        ms = time_op(lambda: (dist.all_reduce(plain), plain.div_(size)), iters, dev)
+        row["nccl_div_us"] = ms * 1e3
+        row["nccl_div_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
+        ms = time_op(lambda: dist.all_reduce(plain), iters, dev)
+        row["nccl_us"] = ms * 1e3
+        row["nccl_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
+        best = min((row[k], k) for k in row if k.endswith("_us") and not k.startswith("nccl"))
+        row["best"] = best[1][:-3]
+        row["speedup_vs_nccl_div"] = row["nccl_div_us"] / best[0]
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+    # the reference's actual pattern: 8 per-tensor all_reduce + 8 divides (ConvNet gradient shapes)
+    shapes = [250, 10, 5000, 20, 16000, 50, 500, 10]
+    grads = [torch.ones(s_, device=dev) for s_ in shapes]
+
+    def ref_avg():
+        for g in grads:
+            dist.all_reduce(g)
+            g.div_(size)
+    per_tensor = time_op(ref_avg, 100, dev) * 1e3
+    bucket = w.alloc(21888, torch.float32)
+    fused = time_op(lambda: w.all_reduce_(bucket.local, scale=1.0 / size, handle=bucket, variant=0), 200, dev) * 1e3
+    if rank == 0:
+        out = {"n_gpus": size, "symm": w.describe(), "rows": rows,
+               "convnet_average_gradients": {"reference_8x(allreduce+div)_us": per_tensor, "fused_oneshot_bucket_us": fused,
+                                             "speedup": per_tensor / fused},
+               "link_GBs_measured_ref": 770, "link_GBs_nominal": 900}
+        os.makedirs(os.path.dirname(ARGS.out) or ".", exist_ok=True)
+        json.dump(out, open(ARGS.out, "w"), indent=1)
+        print("WROTE", ARGS.out, flush=True)
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=2)
+    ap.add_argument("--max-mb", type=int, default=1024)
+    ap.add_argument("--out", default=None)
+    ARGS = ap.parse_args()
+    if ARGS.out is None:
+        ARGS.out = f"gpurun_out/sweep_{ARGS.gpus}.json"
+    if "RANK" in os.environ:
+        b2.init_from_env(body, backend="b200")
+    else:
+        b2.launch(body, size=ARGS.gpus, backend="b200", join_timeout_s=1500)

@@ -20,7 +20,7 @@ namespace cn {
 
 constexpr int W1 = 0, B1 = 252, W2 = 264, B2 = 5264, W3 = 5284, B3 = 21284, W4 = 21336, B4 = 21836;
 constexpr int NPAR = 21848;
-constexpr int T = 256;
+constexpr int T = 512;              // 16 warps per sample: the phases are latency-bound, so more warps per CTA
 
 struct __align__(16) Smem {
   float w1[252];
@@ -32,11 +32,11 @@ struct __align__(16) Smem {
   float b4[12];
   float x[784];
   float p1[1440];           // relu(pool(conv1))  [10][12][12]
-  float part[3 * 1440];     // conv2 partial sums [3][20][64] (3840 used) / dgrad partials [3][10][144]
+  float part[6 * 1440];     // conv2 partial sums [5][20][64] (5*1280 used) / dgrad partials [6][10][144]
   float dc2pad[20 * 256];   // conv2-output gradient, zero padded [20][16][16]
   float p2[320];            // relu(pool(drop(conv2)))  [20][4][4]
   float g2[320];            // gradient at the pooled conv2 argmax
-  float g1[1440];           // gradient at the pooled conv1 argmax
+  float2 g1[1440];          // (gradient at the pooled conv1 argmax, input offset of that position as int bits)
   float h[52];              // fc1 activation after relu+dropout
   float hm[52];             // fc1 backward mask (relu' * dropout scale)
   float dh[52];
@@ -81,18 +81,40 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   const float* __restrict__ P = a.params;
 
   // ---------------------------------------------------------------- P0: stage weights, zero accumulators
-  for (int i = tid; i < 250; i += T) s.w1[i] = P[W1 + i];
-  if (tid < 10) { s.b1[tid] = P[B1 + tid]; s.b4[tid] = P[B4 + tid]; }
-  if (tid < 20) s.b2[tid] = P[B2 + tid];
-  for (int i = tid; i < 500; i += T) s.w4[i] = P[W4 + i];
-  for (int i = tid; i < 5000; i += T) {         // conv2.weight [co][ci][ky][kx]
-    const float w = P[W2 + i];
-    const int co = i / 250, r = i % 250, ci = r / 25, k = r % 25;
-    s.w2f[(ci * 25 + k) * 20 + co] = w;
-    s.w2b[((co * 25 + k) * 2 + ci / 5) * 8 + ci % 5] = w;
+  {
+    // all global loads are issued before their first use (one L2 round trip instead of a dependent chain)
+    const float4* __restrict__ P4w2 = reinterpret_cast<const float4*>(P + W2);   // 1250 float4, 16B aligned
+    float4 v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i4 = tid + k * T;
+      v[k] = i4 < 1250 ? __ldg(P4w2 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float w1v = tid < 250 ? __ldg(P + W1 + tid) : 0.f;
+    const float w4v = tid < 500 ? __ldg(P + W4 + tid) : 0.f;
+    const float bv = tid < 10 ? __ldg(P + B1 + tid) : (tid < 20 ? __ldg(P + B4 + tid - 10) : (tid < 40 ? __ldg(P + B2 + tid - 20) : 0.f));
+    if (a.backward) {
+      float4* g4 = reinterpret_cast<float4*>(s.g);
+      for (int i = tid; i < NPAR / 4; i += T) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < 250) s.w1[tid] = w1v;
+    if (tid < 500) s.w4[tid] = w4v;
+    if (tid < 10) s.b1[tid] = bv; else if (tid < 20) s.b4[tid - 10] = bv; else if (tid < 40) s.b2[tid - 20] = bv;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i4 = tid + k * T;
+      if (i4 < 1250) {
+        const float w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {             // conv2.weight [co][ci][ky][kx]
+          const int i = i4 * 4 + e;
+          const int co = i / 250, r = i % 250, ci = r / 25, kk = r % 25;
+          s.w2f[(ci * 25 + kk) * 20 + co] = w[e];
+          s.w2b[((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = w[e];
+        }
+      }
+    }
   }
-  if (a.backward)
-    for (int i = tid; i < NPAR; i += T) s.g[i] = 0.f;
   if (tid == 0) { s.loss_local = 0.f; s.correct_local = 0; }
   const unsigned long long step = a.step ? *a.step : 0ull;
   const float keep_scale = 1.f / (1.f - a.p_drop);
@@ -101,20 +123,27 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     // -------------------------------------------------------------- S0: input, RNG, clear scratch
     if (a.x_u8) {
-      const unsigned char* xs = reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * 784;
-      for (int i = tid; i < 784; i += T) s.x[i] = ((float)xs[i] * (1.f / 255.f) - a.mean) * a.inv_std;
+      const uint4* xs = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * 784);
+      if (tid < 49) {                              // 784 bytes = 49 x 16
+        const uint4 q = __ldg(xs + tid);
+        const unsigned int wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          s.x[tid * 16 + e] = ((float)((wv[e >> 2] >> ((e & 3) * 8)) & 0xffu) * (1.f / 255.f) - a.mean) * a.inv_std;
+      }
     } else {
-      const float* xs = reinterpret_cast<const float*>(a.x) + (size_t)b * 784;
-      for (int i = tid; i < 784; i += T) s.x[i] = xs[i];
+      const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + (size_t)b * 784);
+      if (tid < 196) reinterpret_cast<float4*>(s.x)[tid] = __ldg(xs + tid);
     }
-    if (tid < 18) {
-      uint4 r = b2::Philox::gen(a.seed, (unsigned long long)(a.sample_base + b), step * 32ull + tid);
+    if (tid >= 256 && tid < 274) {
+      const int q = tid - 256;
+      uint4 r = b2::Philox::gen(a.seed, (unsigned long long)(a.sample_base + b), step * 32ull + q);
       const float k = 2.3283064365386963e-10f;   // 2^-32
-      s.rnd[tid * 4 + 0] = r.x * k; s.rnd[tid * 4 + 1] = r.y * k;
-      s.rnd[tid * 4 + 2] = r.z * k; s.rnd[tid * 4 + 3] = r.w * k;
+      s.rnd[q * 4 + 0] = r.x * k; s.rnd[q * 4 + 1] = r.y * k;
+      s.rnd[q * 4 + 2] = r.z * k; s.rnd[q * 4 + 3] = r.w * k;
     }
     if (a.backward)
-      for (int i = tid; i < 20 * 256; i += T) s.dc2pad[i] = 0.f;
+      for (int i = tid; i < 20 * 256 / 4; i += T) reinterpret_cast<float4*>(s.dc2pad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     // -------------------------------------------------------------- S1: conv1 -> maxpool2 -> relu
@@ -148,11 +177,11 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       s.m2[tid] = a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
     __syncthreads();
 
-    // -------------------------------------------------------------- S2: conv2 partial sums (K split 3)
-    if (tid < 240) {
+    // -------------------------------------------------------------- S2: conv2 partial sums (K split 5)
+    if (tid < 400) {
       const int cell = tid & 15, cg = (tid >> 4) % 5, ks = tid / 80;
       const int py = cell >> 2, px = cell & 3;
-      const int ci0 = (ks == 0) ? 0 : (ks == 1 ? 4 : 7), ci1 = (ks == 0) ? 4 : (ks == 1 ? 7 : 10);
+      const int ci0 = 2 * ks, ci1 = 2 * ks + 2;
       float acc[4][4];
 #pragma unroll
       for (int p = 0; p < 4; ++p)
@@ -192,12 +221,14 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     // -------------------------------------------------------------- S2b: +bias, dropout2d, maxpool2, relu
     for (int o = tid; o < 320; o += T) {
       const int co = o >> 4;
-      const float4 q0 = *reinterpret_cast<const float4*>(&s.part[o * 4]);
-      const float4 q1 = *reinterpret_cast<const float4*>(&s.part[1440 + o * 4]);
-      const float4 q2 = *reinterpret_cast<const float4*>(&s.part[2880 + o * 4]);
+      float4 q = *reinterpret_cast<const float4*>(&s.part[o * 4]);
+#pragma unroll
+      for (int ks = 1; ks < 5; ++ks) {
+        const float4 t = *reinterpret_cast<const float4*>(&s.part[ks * 1440 + o * 4]);
+        q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+      }
       const float bias = s.b2[co], sc = s.m2[co];
-      const float v0 = (q0.x + q1.x + q2.x + bias) * sc, v1 = (q0.y + q1.y + q2.y + bias) * sc;
-      const float v2 = (q0.z + q1.z + q2.z + bias) * sc, v3 = (q0.w + q1.w + q2.w + bias) * sc;
+      const float v0 = (q.x + bias) * sc, v1 = (q.y + bias) * sc, v2 = (q.z + bias) * sc, v3 = (q.w + bias) * sc;
       float m = v0; int arg = 0;
       if (v1 > m) { m = v1; arg = 1; }
       if (v2 > m) { m = v2; arg = 2; }
@@ -208,9 +239,8 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     __syncthreads();
 
     // -------------------------------------------------------------- S3: fc1 + relu + dropout
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int j = (tid >> 3) + 32 * pass, l8 = tid & 7;
+    {
+      const int j = tid >> 3, l8 = tid & 7;
       float sum = 0.f;
       if (j < 50) {
         const float4* wrow = reinterpret_cast<const float4*>(P + W3 + j * 320);
@@ -286,13 +316,17 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 
     // -------------------------------------------------------------- S6: fc1 backward
     {
-      int j = 0, i = tid;                         // e = j*320 + i, e = tid + 256*m
-      for (int e = tid; e < 16000; e += T) {
-        s.g[W3 + e] += s.dh[j] * s.p2[i];
-        i += T;
-        if (i >= 320) { i -= 320; ++j; }
+      float4* gw3 = reinterpret_cast<float4*>(&s.g[W3]);
+      const float4* p24 = reinterpret_cast<const float4*>(s.p2);
+      for (int e4 = tid; e4 < 4000; e4 += T) {    // fc1.weight gradient: 4 consecutive inputs per thread-iteration
+        const int j = e4 / 80, i4 = e4 - j * 80;
+        const float d = s.dh[j];
+        const float4 pv = p24[i4];
+        float4 gv = gw3[e4];
+        gv.x = fmaf(d, pv.x, gv.x); gv.y = fmaf(d, pv.y, gv.y); gv.z = fmaf(d, pv.z, gv.z); gv.w = fmaf(d, pv.w, gv.w);
+        gw3[e4] = gv;
       }
-      if (tid < 50) s.g[B3 + tid] += s.dh[tid];
+      if (tid >= 320 && tid < 370) s.g[B3 + tid - 320] += s.dh[tid - 320];
       for (int o = tid; o < 320; o += T) {
         float d = 0.f;
 #pragma unroll 10
@@ -307,38 +341,36 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     __syncthreads();
 
     // -------------------------------------------------------------- S7a: conv2 weight/bias gradient (sparse)
-    if (tid < 200) {
-      const int co = tid / 10, ci = tid % 10;
-      float acc[25];
-#pragma unroll
-      for (int k = 0; k < 25; ++k) acc[k] = 0.f;
+    for (int item = tid; item < 1000; item += T) {          // item = (co, ci, ky): 5 taps (kx) x 16 pooled cells
+      const int co = item / 50, r = item - co * 50, ci = r / 5, ky = r - ci * 5;
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
       for (int cell = 0; cell < 16; ++cell) {
         const float gv = s.g2[co * 16 + cell];
         if (gv != 0.f) {
           const int arg = s.a2[co * 16 + cell];
           const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
-          const float* src = &s.p1[ci * 144 + ay * 12 + ax];
+          const float* src = &s.p1[ci * 144 + (ay + ky) * 12 + ax];
 #pragma unroll
-          for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 5; ++kx) acc[ky * 5 + kx] = fmaf(gv, src[ky * 12 + kx], acc[ky * 5 + kx]);
+          for (int kx = 0; kx < 5; ++kx) acc[kx] = fmaf(gv, src[kx], acc[kx]);
         }
       }
-      float* dst = &s.g[W2 + co * 250 + ci * 25];
+      float* dst = &s.g[W2 + co * 250 + ci * 25 + ky * 5];
 #pragma unroll
-      for (int k = 0; k < 25; ++k) dst[k] += acc[k];
-    } else if (tid < 220) {
-      const int co = tid - 200;
+      for (int kx = 0; kx < 5; ++kx) dst[kx] += acc[kx];
+    }
+    if (tid >= 488 && tid < 508) {                          // idle lanes of the second pass: bias gradient
+      const int co = tid - 488;
       float d = 0.f;
 #pragma unroll
       for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
       s.g[B2 + co] += d;
     }
-    // -------------------------------------------------------------- S7b: conv2 data gradient (dense, K split 3)
-    if (tid < 216) {
+    // -------------------------------------------------------------- S7b: conv2 data gradient (dense, K split 6)
+    if (tid < 432) {
       const int tile = tid % 36, half = (tid / 36) & 1, ks = tid / 72;
       const int y0 = 2 * (tile / 6), x0 = 2 * (tile % 6);
-      const int co0 = ks * 7, co1 = ks == 2 ? 20 : co0 + 7;
+      const int co0 = ks < 2 ? 4 * ks : 8 + 3 * (ks - 2), co1 = ks < 2 ? co0 + 4 : co0 + 3;   // 4,4,3,3,3,3
       float acc[4][5];
 #pragma unroll
       for (int p = 0; p < 4; ++p)
@@ -380,25 +412,36 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     __syncthreads();
 
     // -------------------------------------------------------------- S8a: through relu+pool of conv1
-    for (int o = tid; o < 1440; o += T)
-      s.g1[o] = s.p1[o] > 0.f ? (s.part[o] + s.part[1440 + o] + s.part[2880 + o]) : 0.f;
+    for (int o = tid; o < 1440; o += T) {
+      float d = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) d += s.part[ks * 1440 + o];
+      const int cell = o % 144, arg = s.a1[o];
+      const int off = (2 * (cell / 12) + (arg >> 1)) * 28 + 2 * (cell % 12) + (arg & 1);
+      s.g1[o] = make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off));
+    }
     __syncthreads();
 
     // -------------------------------------------------------------- S8b: conv1 weight/bias gradient (sparse)
-    if (tid < 250) {
-      const int c = tid / 25, k = tid % 25, ky = k / 5, kx = k % 5;
+    {
+      const int out = tid >> 1, half = tid & 1;              // two lanes per tap: 72 cells each
       float acc = 0.f;
-      for (int cell = 0; cell < 144; ++cell) {
-        const float gv = s.g1[c * 144 + cell];
-        const int arg = s.a1[c * 144 + cell];
-        const int y = 2 * (cell / 12) + (arg >> 1) + ky, x = 2 * (cell % 12) + (arg & 1) + kx;
-        acc = fmaf(gv, s.x[y * 28 + x], acc);
+      if (tid < 500) {
+        const int c = out / 25, k = out - c * 25, koff = (k / 5) * 28 + (k % 5);
+        const float2* gp = &s.g1[c * 144 + half * 72];
+#pragma unroll 8
+        for (int cell = 0; cell < 72; ++cell) {
+          const float2 q = gp[cell];
+          acc = fmaf(q.x, s.x[__float_as_int(q.y) + koff], acc);
+        }
       }
-      s.g[W1 + tid] += acc;
-    } else if (tid - 250 < 6) {                   // 6 threads do the 10 bias sums (250..255)
-      for (int c = tid - 250; c < 10; c += 6) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);           // executed by every lane (no divergence at the shuffle)
+      if (tid < 500) {
+        if (half == 0) s.g[W1 + out] += acc;
+      } else if (tid < 510) {
+        const int c = tid - 500;
         float d = 0.f;
-        for (int cell = 0; cell < 144; ++cell) d += s.g1[c * 144 + cell];
+        for (int cell = 0; cell < 144; ++cell) d += s.g1[c * 144 + cell].x;
         s.g[B1 + c] += d;
       }
     }

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Distributed synchronous SGD on (synthetic) MNIST -- the reference's ``train_dist.py`` scenario.
+
+    python examples/train_mnist.py                       # CPU, gloo, world 2 (the reference default)
+    python examples/train_mnist.py --backend b200 --size 8     # one process per B200, fused engine
+    torchrun --nproc-per-node 8 examples/train_mnist.py --backend b200 --external
+
+Prints ``Rank r, epoch e: mean loss`` per epoch like train_dist.py:125-127."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dist_tuto.pth_b200 as dist  # noqa: E402
+
+CFG = {}
+
+
+def run(rank, size):
+    cfg = dist.TrainConfig(epochs=CFG["epochs"], lr=CFG["lr"], max_steps=CFG["max_steps"], checkpoint=CFG["ckpt"])
+    out = dist.train(rank, size, cfg)
+    if rank == 0:
+        print(f"{out['steps']} steps, {out['samples_per_s']:.0f} samples/s (wall clock, whole job)")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=2)
+    ap.add_argument("--backend", default="gloo")
+    ap.add_argument("--epochs", type=int, default=10)
+    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--checkpoint", default=None)
+    ap.add_argument("--external", action="store_true", help="rank/size from torchrun/mpirun env")
+    a = ap.parse_args()
+    CFG.update(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint)
+    if a.external:
+        dist.init_from_env(run, backend=a.backend)
+    else:
+        dist.launch(run, size=a.size, backend=a.backend)

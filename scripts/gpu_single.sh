@@ -11,7 +11,7 @@ echo "== bench ours"; timeout 600 python bench.py --gpus 1 --steps 400 --warmup 
 echo "== bench ref"; timeout 600 python bench.py --impl reference --gpus 1 --steps 400 --warmup 20 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 1500 $OUT/bench_ref.json; tail -5 $OUT/bench_ref.err
 echo "== kernel microbench"; timeout 600 python bench/kernel_bench.py > $OUT/kernel_bench.json 2> $OUT/kernel_bench.err; tail -c 3000 $OUT/kernel_bench.json; tail -5 $OUT/kernel_bench.err
 echo "== ncu launches"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file $OUT/launches.csv python bench.py --gpus 1 --steps 20 --warmup 5 --graph-chunk 1 --no-e2e > $OUT/ncu_launch.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"convnet_step|allreduce_sgd" -s 10 -c 40 --csv --log-file $OUT/launches.csv python bench.py --gpus 1 --steps 20 --warmup 5 --graph-chunk 1 --no-e2e > $OUT/ncu_launch.log 2>&1
 tail -3 $OUT/launches.csv
 echo "== ncu full (convnet_step)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:convnet_step -s 6 -c 2 -o $OUT/prof_convnet -f python bench.py --gpus 1 --steps 8 --warmup 3 --graph-chunk 1 --no-e2e > $OUT/ncu_full.log 2>&1
