@@ -20,7 +20,8 @@ sys.path.insert(0, ROOT)
 import dist_tuto.pth_b200 as b2  # noqa: E402
 from dist_tuto.pth_b200.parallel import symm  # noqa: E402
 
-ARGS = None
+import types
+ARGS = types.SimpleNamespace(**json.loads(os.environ["B2_BENCH_ARGS"])) if "B2_BENCH_ARGS" in os.environ else None
 
 
 def tmax(ms, dev):
@@ -114,6 +115,7 @@ if __name__ == "__main__":
     ARGS = ap.parse_args()
     if ARGS.out is None:
         ARGS.out = f"gpurun_out/sweep_{ARGS.gpus}.json"
+    os.environ["B2_BENCH_ARGS"] = json.dumps(vars(ARGS))
     if "RANK" in os.environ:
         b2.init_from_env(body, backend="b200")
     else:

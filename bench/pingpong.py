@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dist_tuto.pth_b200 as b2  # noqa: E402
 
-ARGS = None
+import types
+ARGS = types.SimpleNamespace(**json.loads(os.environ["B2_BENCH_ARGS"])) if "B2_BENCH_ARGS" in os.environ else None
 
 
 def body(rank, size):
@@ -63,4 +64,5 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/pingpong.json")
     ARGS = ap.parse_args()
+    os.environ["B2_BENCH_ARGS"] = json.dumps(vars(ARGS))
     b2.launch(body, size=2, backend="nccl", join_timeout_s=600)

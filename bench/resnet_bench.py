@@ -21,7 +21,8 @@ import dist_tuto.pth_b200 as b2  # noqa: E402
 from dist_tuto.pth_b200.models.resnet import ResNet18  # noqa: E402
 from dist_tuto.pth_b200.parallel.ddp import DistributedDataParallel  # noqa: E402
 
-ARGS = None
+import types
+ARGS = types.SimpleNamespace(**json.loads(os.environ["B2_BENCH_ARGS"])) if "B2_BENCH_ARGS" in os.environ else None
 
 
 def run_mode(mode, rank, size, dev):
@@ -97,6 +98,7 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=None)
     ARGS = ap.parse_args()
     ARGS.out = ARGS.out or f"gpurun_out/resnet_{ARGS.gpus}.json"
+    os.environ["B2_BENCH_ARGS"] = json.dumps(vars(ARGS))
     if "RANK" in os.environ:
         b2.init_from_env(body, backend="b200")
     else:

@@ -21,7 +21,9 @@
 
 namespace gemm {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
+// stages sized so that TWO CTAs fit per SM (<= ~113 KB each): one CTA's epilogue/prologue overlaps the other's mainloop
+template <int BN> struct Cfg { static constexpr int STAGES = BN >= 128 ? 3 : 4; };
 constexpr int kThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +86,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 
 template <int BN>
 struct SmemLayout {
+  static constexpr int STAGES = Cfg<BN>::STAGES;
   alignas(1024) uint8_t a[STAGES][BM * BK * 2];
   alignas(1024) uint8_t b[STAGES][BN * BK * 2];
   alignas(8) uint64_t full[STAGES];
@@ -93,7 +96,7 @@ struct SmemLayout {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ c,
                  const float* __restrict__ bias, int M, int N, int K, int relu, int out_bf16) {
   extern __shared__ uint8_t smem_raw[];
@@ -101,6 +104,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_kb = (K + BK - 1) / BK;
+  constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;       // power of two >= 32
   constexpr uint32_t kStageBytes = (BM + BN) * BK * 2;
 

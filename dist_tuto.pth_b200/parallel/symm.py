@@ -20,6 +20,7 @@ same order on every rank of the world (as with any communicator).
 """
 from __future__ import annotations
 
+import array
 import os
 import socket
 import struct
@@ -134,7 +135,9 @@ class SymmWorld:
         if self.rank in senders:
             for r in range(self.world):
                 if r != self.rank:
-                    socket.send_fds(self._sock, [struct.pack("ii", tag, self.rank)], [fd], 0, self._addr(r))
+                    # (socket.send_fds ignores its address argument on CPython <= 3.12, so use sendmsg directly)
+                    self._sock.sendmsg([struct.pack("ii", tag, self.rank)],
+                                       [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", [fd]))], 0, self._addr(r))
         got: Dict[int, int] = {}
         expect = [s for s in senders if s != self.rank]
         while len(got) < len(expect):

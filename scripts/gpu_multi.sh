@@ -5,7 +5,10 @@ N=${1:-2}
 OUT=gpurun_out/multi$N
 mkdir -p $OUT
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
-echo "== tests"; timeout 1500 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider 2>&1 | tail -60 > $OUT/pytest.txt; tail -25 $OUT/pytest.txt
+echo "== core test (fail fast)"
+timeout 420 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider -k symmetric_allreduce 2>&1 | tail -60 > $OUT/pytest_core.txt; tail -25 $OUT/pytest_core.txt
+if ! grep -q "1 passed" $OUT/pytest_core.txt; then echo "CORE TEST FAILED -- skipping the rest"; ls -la $OUT; exit 1; fi
+echo "== tests"; timeout 1200 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider -k "not symmetric_allreduce" 2>&1 | tail -60 > $OUT/pytest.txt; tail -25 $OUT/pytest.txt
 echo "== sweep"; timeout 900 python bench/allreduce_sweep.py --gpus $N --max-mb ${2:-256} --out $OUT/sweep.json > $OUT/sweep.log 2>&1; tail -12 $OUT/sweep.log
 if [ "$N" = "2" ]; then echo "== pingpong"; timeout 300 python bench/pingpong.py --out $OUT/pingpong.json > $OUT/pingpong.log 2>&1; tail -8 $OUT/pingpong.log; fi
 for n in $(seq 1 $N); do
