@@ -49,6 +49,8 @@ def main():
     hbm, flops, src = peaks()
     out = {"peaks": {"hbm_Bps": hbm, "bf16_flops": flops, "source": src}, "gemm": [], "convnet": []}
     shapes = [(128, 64, 320), (8192, 32, 256), (4096, 512, 1024), (8192, 4096, 4096), (16384, 1000, 512)]
+    if "--big-only" in sys.argv:
+        shapes = [(8192, 4096, 4096)]
     for M, N, K in shapes:
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)

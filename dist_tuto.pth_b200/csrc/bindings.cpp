@@ -5,10 +5,13 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "executor.h"
 #include "loader.h"
 
 #define B2_MAX_RANKS 8
@@ -52,6 +55,7 @@ int b2_gemm_available();
 int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias, int M, int N, int K, int relu,
                         int out_bf16, cudaStream_t stream);
 const char* b2_gemm_last_error();
+int b2_gemm_probe_m64(const void* a, const void* b, float* dump, cudaStream_t stream);
 }
 
 namespace {
@@ -121,6 +125,47 @@ struct LoaderPy {
     }
     if (slot < 0) return py::none();
     return py::make_tuple(xs[slot].narrow(0, 0, count), ys[slot].narrow(0, 0, count));
+  }
+};
+
+struct ExecutorPy {
+  std::unique_ptr<b2::StepExecutor> impl;
+  LoaderPy* loader;
+  std::vector<torch::Tensor> keep;
+  ExecutorPy(LoaderPy& l, torch::Tensor params, torch::Tensor momentum, torch::Tensor grads,
+             std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
+             torch::Tensor loss_acc, torch::Tensor x_dev, torch::Tensor y_dev, bool training, int rank, int world,
+             uint64_t seed, int64_t sample_base, double lr, double mu, double p_drop, int max_in_flight)
+      : loader(&l), keep{params, momentum, grads, step, loss_acc, x_dev, y_dev} {
+    TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
+    TORCH_CHECK(l.impl->batch() == y_dev.numel(), "loader batch != trainer batch");
+    TORCH_CHECK((x_dev.scalar_type() == torch::kUInt8) == l.impl->raw(), "loader / trainer input dtype mismatch");
+    b2::StepConfig c;
+    std::memset(&c, 0, sizeof(c));
+    c.params = params.data_ptr<float>(); c.momentum = momentum.data_ptr<float>(); c.grads_local = grads.data_ptr<float>();
+    for (size_t i = 0; i < grad_ptrs.size() && i < 8; ++i) c.grad_ptrs[i] = (void*)(uintptr_t)grad_ptrs[i];
+    for (size_t i = 0; i < sig_ptrs.size() && i < 8; ++i) c.sig_ptrs[i] = (uint32_t*)(uintptr_t)sig_ptrs[i];
+    c.step_counter = reinterpret_cast<unsigned long long*>(step.data_ptr());
+    c.loss_acc = loss_acc.data_ptr<float>();
+    c.x_dev = x_dev.data_ptr(); c.y_dev = reinterpret_cast<long long*>(y_dev.data_ptr<int64_t>());
+    c.B = (int)y_dev.numel(); c.x_u8 = x_dev.scalar_type() == torch::kUInt8; c.training = training;
+    c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base;
+    c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop;
+    const int cap = std::max(1, l.impl->num_slots() - 2);
+    c10::cuda::CUDAGuard guard(params.device());
+    impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
+  }
+  py::tuple run(int64_t max_steps) {
+    int pending = -1, epoch_done = 0;
+    int64_t count = 0, done;
+    {
+      py::gil_scoped_release nogil;
+      done = impl->run(max_steps, &pending, &count, &epoch_done);
+    }
+    if (done < 0) throw std::runtime_error("StepExecutor: " + impl->error());
+    py::object tail = py::none();
+    if (pending >= 0) tail = py::make_tuple(loader->xs[pending].narrow(0, 0, count), loader->ys[pending].narrow(0, 0, count));
+    return py::make_tuple(done, tail, epoch_done != 0);
   }
 };
 
@@ -239,6 +284,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (rc != 0) throw std::runtime_error(std::string("gemm_bf16: ") + b2_gemm_last_error());
     return c;
   }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("relu") = false, py::arg("out_bf16") = true);
+
+  m.def("gemm_probe_m64", [](torch::Tensor a, torch::Tensor b) {
+    check_cuda_contig(a, "a"); check_cuda_contig(b, "b");
+    TORCH_CHECK(a.scalar_type() == torch::kBFloat16 && a.size(0) == 64 && a.size(1) == 64 && b.size(0) == 32 && b.size(1) == 64);
+    auto dump = torch::zeros({128, 32}, a.options().dtype(torch::kFloat32));
+    int rc = b2_gemm_probe_m64(a.data_ptr(), b.data_ptr(), dump.data_ptr<float>(), cur_stream());
+    if (rc != 0) throw std::runtime_error(std::string("gemm_probe_m64: ") + b2_gemm_last_error());
+    return dump;
+  });
+
+  // ------------------------------------------------------------------ native step executor
+  py::class_<ExecutorPy>(m, "StepExecutor")
+      .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
+                    std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool,
+                    int, int, uint64_t, int64_t, double, double, double, int>(),
+           py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
+           py::arg("sig_ptrs"), py::arg("step"), py::arg("loss_acc"), py::arg("x_dev"), py::arg("y_dev"),
+           py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"), py::arg("sample_base"),
+           py::arg("lr"), py::arg("mu"), py::arg("p_drop"), py::arg("max_in_flight") = 3, py::keep_alive<1, 2>())
+      .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
+      .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
+      .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });
 
   // ------------------------------------------------------------------ native loader
   py::class_<LoaderPy>(m, "NativeLoader")

@@ -425,24 +425,25 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     // -------------------------------------------------------------- S8b: conv1 weight/bias gradient (sparse)
     {
       const int out = tid >> 1, half = tid & 1;              // two lanes per tap: 72 cells each
-      float acc = 0.f;
+      float acc = 0.f, gsum = 0.f;
+      int k = 0;
       if (tid < 500) {
-        const int c = out / 25, k = out - c * 25, koff = (k / 5) * 28 + (k % 5);
+        const int c = out / 25;
+        k = out - c * 25;
+        const int koff = (k / 5) * 28 + (k % 5);
         const float2* gp = &s.g1[c * 144 + half * 72];
 #pragma unroll 8
         for (int cell = 0; cell < 72; ++cell) {
           const float2 q = gp[cell];
+          gsum += q.x;                                       // bias gradient rides along (used by the k == 0 lanes)
           acc = fmaf(q.x, s.x[__float_as_int(q.y) + koff], acc);
         }
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);           // executed by every lane (no divergence at the shuffle)
-      if (tid < 500) {
-        if (half == 0) s.g[W1 + out] += acc;
-      } else if (tid < 510) {
-        const int c = tid - 500;
-        float d = 0.f;
-        for (int cell = 0; cell < 144; ++cell) d += s.g1[c * 144 + cell].x;
-        s.g[B1 + c] += d;
+      gsum += __shfl_xor_sync(0xffffffffu, gsum, 1);
+      if (tid < 500 && half == 0) {
+        s.g[W1 + out] += acc;
+        if (k == 0) s.g[B1 + out / 25] += gsum;
       }
     }
     __syncthreads();

@@ -221,6 +221,73 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ M=64 layout probe
+// D[64 x 32] = A[64 x 64] * B[32 x 64]^T with a UMMA_M = 64 instruction; the kernel zero-fills TMEM first and then
+// dumps all 128 TMEM lanes x 32 columns, so the host can read off which lane holds which accumulator row.
+__global__ void __launch_bounds__(128, 1)
+probe_m64_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ dump) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = base;                 // 64 x 128 B
+  uint8_t* sb = base + 8192;          // 32 x 128 B
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + 8192 + 4096);
+  uint64_t* done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1); mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  {   // zero all 128 lanes x 32 columns
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + c0), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(full, 8192 + 4096);
+    tma_load_2d(sa, &map_a, full, 0, 0);
+    tma_load_2d(sb, &map_b, full, 0, 0);
+    mbar_wait(full, 0);
+    tcgen05_fence_after();
+    constexpr uint32_t idesc = make_idesc(64, 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, make_smem_desc(smem_u32(sa) + k * 32), make_smem_desc(smem_u32(sb) + k * 32), idesc, k > 0 ? 1u : 0u);
+    tcgen05_commit(done);
+  }
+  __syncwarp();
+  mbar_wait(done, 0);
+  tcgen05_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dump[(warp * 32 + lane) * 32 + c0 + i] = __uint_as_float(r[i]);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 std::string g_err;
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -277,6 +344,16 @@ int launch(const void* a, const void* b, void* c, const float* bias, int M, int 
 }  // namespace gemm
 
 extern "C" {
+
+// a: [64,64] bf16, b: [32,64] bf16, dump: [128,32] fp32
+int b2_gemm_probe_m64(const void* a, const void* b, float* dump, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  if (!gemm::make_map(&ma, a, 64, 64, 64) || !gemm::make_map(&mb, b, 32, 64, 32)) return -1;
+  const size_t smem = 8192 + 4096 + 64 + 1024;
+  cudaFuncSetAttribute(gemm::probe_m64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gemm::probe_m64_kernel<<<1, 128, smem, stream>>>(ma, mb, dump);
+  return (int)cudaGetLastError();
+}
 
 int b2_gemm_available() { return gemm::get_encode() != nullptr; }
 const char* b2_gemm_last_error() { return gemm::g_err.c_str(); }

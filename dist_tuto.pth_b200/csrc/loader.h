@@ -25,6 +25,7 @@ class NativeLoader {
   void release();
   void stop();
   const Slot& slot(int i) const { return slots_[i]; }
+  int num_slots() const { return nbuf_; }
   int64_t batch() const { return batch_; }
   int64_t item() const { return item_; }
   bool raw() const { return raw_; }

@@ -308,6 +308,11 @@ class NativeBatchLoader:
     def __len__(self) -> int:
         return int(self._l.num_batches())
 
+    def begin_epoch(self) -> None:
+        """Start the prefetch thread on a freshly shuffled epoch (used by the native step executor)."""
+        self._l.start_epoch(self._epoch)
+        self._epoch += 1
+
     def __iter__(self):
         self._l.start_epoch(self._epoch)
         self._epoch += 1

@@ -138,6 +138,7 @@ class FusedTrainer:
             s.loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
             s.graph, s.event, s.busy = None, torch.cuda.Event(), False
             self.slots.append(s)
+        self._executors = {}                        # id(loader) -> (C++ StepExecutor, training flag)
         self._ext_slots: Dict[int, _Slot] = {}      # loader-owned pinned buffers -> their graphs
         self._order = deque()                       # slots in flight, oldest first
         self._nstep = 0
@@ -219,9 +220,13 @@ class FusedTrainer:
         if s.graph is None:
             self.sync_lag(0)
             self._capture(s)
-        with torch.cuda.stream(self.stream):
+        if torch.cuda.current_stream(self.device) == self.stream:     # fast path: caller already runs on our stream
             s.graph.replay()
             s.event.record(self.stream)
+        else:
+            with torch.cuda.stream(self.stream):
+                s.graph.replay()
+                s.event.record(self.stream)
         s.busy = True
         self._order.append(s)
         self._nstep += 1
@@ -233,12 +238,45 @@ class FusedTrainer:
         with torch.cuda.stream(self.stream):
             x = data.to(self.device, non_blocking=True).contiguous()
             y = target.to(self.device, non_blocking=True).contiguous()
-            if (x.dtype == torch.uint8) != self.raw_uint8 and x.dtype != torch.uint8:
+            if x.dtype not in (torch.uint8, torch.float32):
                 x = x.to(torch.float32)
             self._kernels(x, y, B)
         self.stream.synchronize()
         self._last_loss_cum = float(self.loss_acc[0].item())
         self._nstep += 1
+
+    def active(self):
+        """Context manager that makes the trainer's stream current (removes per-step stream switching)."""
+        return torch.cuda.stream(self.stream)
+
+    # ------------------------------------------------------------------ native hot loop
+    def run_native(self, loader, max_steps: Optional[int] = None, new_epoch: bool = True):
+        """Run (part of) an epoch with the C++ step executor (csrc/executor.cpp): no Python in the loop.
+
+        ``loader`` is a :class:`data.NativeBatchLoader` with ``batch_size == bsz`` and a dtype matching
+        ``raw_uint8``.  Returns ``(steps_done, epoch_finished)``.  A short tail batch is processed eagerly."""
+        self.sync_lag(0)
+        self.stream.synchronize()
+        ex = self._executors.get(id(loader))
+        if ex is None or ex[1] != self.training:
+            ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
+                                      self.step_counter, self.loss_acc, self.x_dev, self.y_dev, self.training, self.rank,
+                                      self.world, self.seed, self.rank * self.bsz, self.lr, self.mu, self.p_drop,
+                                      max(1, loader.num_buffers - 2)), self.training)
+            self._executors[id(loader)] = ex
+        if new_epoch:
+            loader.begin_epoch()
+        done, tail, finished = ex[0].run(-1 if max_steps is None else int(max_steps))
+        self._nstep += done
+        if tail is not None:
+            ex[0].drain()
+            self._eager_step(tail[0], tail[1], tail[1].numel())
+            loader._l.release()
+            done += 1
+            finished = True                      # a short batch is always the last one of the epoch
+        ex[0].drain()
+        self._last_loss_cum = ex[0].last_loss_cumulative() if done else self._last_loss_cum
+        return done, finished
 
     def pop_loss_sum(self) -> float:
         """Sum of per-batch mean losses since the previous call (one sync)."""

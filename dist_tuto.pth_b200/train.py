@@ -64,12 +64,14 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     engine = cfg.engine
     if engine == "auto":
         engine = "fused" if device.type == "cuda" else "torch"
-    train_set, bsz = partition_dataset(cfg.dataset, global_batch=cfg.global_batch, seed=cfg.seed)
+    fused_raw = engine == "fused" and (cfg.dataset is None or hasattr(cfg.dataset, "images"))
+    train_set, bsz = partition_dataset(cfg.dataset, global_batch=cfg.global_batch, seed=cfg.seed,
+                                       **({"raw_uint8": True} if fused_raw else {}))
     num_batches = ceil(len(train_set.dataset) / float(bsz))      # train_dist.py:112
     if engine == "fused":
         from .ops.convnet_fused import FusedTrainer
         trainer = FusedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
-                               p_drop=cfg.p_drop)
+                               p_drop=cfg.p_drop, raw_uint8=fused_raw)
         if cfg.resume:
             trainer.load_state_dict(torch.load(cfg.resume, map_location="cpu"))
         step_fn, epoch_loss_fn, model = trainer.step, trainer.pop_loss_sum, trainer
@@ -100,16 +102,23 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
 
     history, steps, t0 = [], 0, time.perf_counter()
     done = False
+    native_loop = engine == "fused" and hasattr(train_set, "begin_epoch") and torch.cuda.is_available()
     for epoch in range(cfg.epochs):
         model.train()
         nb = 0
-        for data, target in train_set:
-            step_fn(data, target)
-            steps += 1
-            nb += 1
-            if cfg.max_steps is not None and steps >= cfg.max_steps:
-                done = True
-                break
+        if native_loop:       # C++ executor: prefetch thread -> cudaGraphLaunch per step, no Python in the loop
+            budget = None if cfg.max_steps is None else cfg.max_steps - steps
+            nb, _ = trainer.run_native(train_set, max_steps=budget)
+            steps += nb
+            done = cfg.max_steps is not None and steps >= cfg.max_steps
+        else:
+            for data, target in train_set:
+                step_fn(data, target)
+                steps += 1
+                nb += 1
+                if cfg.max_steps is not None and steps >= cfg.max_steps:
+                    done = True
+                    break
         denom = num_batches if not done else max(nb, 1)
         mean_loss = epoch_loss_fn() / denom
         history.append(mean_loss)

@@ -15,5 +15,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 tail -3 $OUT/launches.csv
 echo "== ncu full (convnet_step)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:convnet_step -s 6 -c 2 -o $OUT/prof_convnet -f python bench.py --gpus 1 --steps 8 --warmup 3 --graph-chunk 1 --no-e2e > $OUT/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o $OUT/prof_gemm -f python bench/kernel_bench.py --gemm-only > $OUT/ncu_gemm.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 4 -c 1 -o $OUT/prof_gemm -f python bench/kernel_bench.py --gemm-only --big-only > $OUT/ncu_gemm.log 2>&1
 ls -la $OUT
