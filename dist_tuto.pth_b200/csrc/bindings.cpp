@@ -42,7 +42,7 @@ int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const Signa
 int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t stream);
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, cudaStream_t stream);
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -50,7 +50,9 @@ int b2_convnet_npar();
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, cudaStream_t stream);
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream);
+void b2_convnet_set_tc(int on);
+int b2_convnet_get_tc();
 int b2_gemm_available();
 int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias, int M, int N, int K, int relu,
                         int out_bf16, cudaStream_t stream);
@@ -134,22 +136,26 @@ struct ExecutorPy {
   std::vector<torch::Tensor> keep;
   ExecutorPy(LoaderPy& l, torch::Tensor params, torch::Tensor momentum, torch::Tensor grads,
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
-             torch::Tensor loss_acc, torch::Tensor x_dev, torch::Tensor y_dev, bool training, int rank, int world,
-             uint64_t seed, int64_t sample_base, double lr, double mu, double p_drop, int max_in_flight)
-      : loader(&l), keep{params, momentum, grads, step, loss_acc, x_dev, y_dev} {
+             torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
+             int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
+             int max_in_flight)
+      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
-    TORCH_CHECK(l.impl->batch() == y_dev.numel(), "loader batch != trainer batch");
-    TORCH_CHECK((x_dev.scalar_type() == torch::kUInt8) == l.impl->raw(), "loader / trainer input dtype mismatch");
+    TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
+    const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
+    TORCH_CHECK(in_dev.is_cuda() && in_dev.scalar_type() == torch::kUInt8 && (size_t)in_dev.numel() >= 2 * block,
+                "in_dev: CUDA uint8 buffer of >= 2 * block bytes");
     b2::StepConfig c;
     std::memset(&c, 0, sizeof(c));
     c.params = params.data_ptr<float>(); c.momentum = momentum.data_ptr<float>(); c.grads_local = grads.data_ptr<float>();
     for (size_t i = 0; i < grad_ptrs.size() && i < 8; ++i) c.grad_ptrs[i] = (void*)(uintptr_t)grad_ptrs[i];
     for (size_t i = 0; i < sig_ptrs.size() && i < 8; ++i) c.sig_ptrs[i] = (uint32_t*)(uintptr_t)sig_ptrs[i];
     c.step_counter = reinterpret_cast<unsigned long long*>(step.data_ptr());
+    c.done_counter = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
     c.loss_acc = loss_acc.data_ptr<float>();
-    c.x_dev = x_dev.data_ptr(); c.y_dev = reinterpret_cast<long long*>(y_dev.data_ptr<int64_t>());
-    c.B = (int)y_dev.numel(); c.x_u8 = x_dev.scalar_type() == torch::kUInt8; c.training = training;
-    c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base;
+    c.in_dev[0] = in_dev.data_ptr<uint8_t>(); c.in_dev[1] = in_dev.data_ptr<uint8_t>() + block;
+    c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
+    c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;
     c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop;
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
@@ -219,15 +225,21 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("allreduce_sgd", [](std::vector<unsigned long long> grads, std::vector<unsigned long long> sigs, torch::Tensor params,
                             torch::Tensor momentum, c10::optional<torch::Tensor> step, double lr, double mu, double scale,
-                            int rank, int world, bool zero_grads) {
+                            int rank, int world, bool zero_grads, int64_t grad_stride, c10::optional<torch::Tensor> done_counter) {
     check_cuda_contig(params, "params"); check_cuda_contig(momentum, "momentum");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && momentum.scalar_type() == torch::kFloat32, "fp32 flat buffers");
     TORCH_CHECK(params.numel() % 4 == 0 && params.numel() == momentum.numel(), "flat buffers must be padded to 4 elements");
     PeerPtrs g = to_ptrs(grads); SignalPadsH s = to_sig(sigs);
     unsigned long long* st = step.has_value() ? reinterpret_cast<unsigned long long*>(step->data_ptr()) : nullptr;
+    unsigned int* dc = done_counter.has_value() ? reinterpret_cast<unsigned int*>(done_counter->data_ptr()) : nullptr;
+    TORCH_CHECK(st == nullptr || dc != nullptr, "a step counter needs a done_counter scratch word");
+    c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
-                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, cur_stream()), "allreduce_sgd launch");
-  });
+                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, cur_stream()),
+            "allreduce_sgd launch");
+  }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
+     py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
+     py::arg("done_counter") = py::none());
   m.def("sgd_flat", [](torch::Tensor p, torch::Tensor mom, torch::Tensor g, double lr, double mu, double wd, bool zero_grad) {
     check_cuda_contig(p, "p"); check_cuda_contig(mom, "m"); check_cuda_contig(g, "g");
     TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
@@ -239,11 +251,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   // ------------------------------------------------------------------ fused ConvNet step
   m.def("convnet_npar", [] { return b2_convnet_npar(); });
+  m.def("convnet_set_tc", [](bool on) { b2_convnet_set_tc(on); }, "route conv2 forward/dgrad of the fused step through tcgen05 (bf16)");
+  m.def("convnet_get_tc", [] { return b2_convnet_get_tc() != 0; });
   m.def("convnet_smem_bytes", [] { return b2_convnet_smem_bytes(); });
   m.def("convnet_step", [](torch::Tensor params, c10::optional<torch::Tensor> grads, torch::Tensor x, torch::Tensor target,
                            c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
                            c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
-                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas) {
+                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride) {
     check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
     TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
@@ -252,7 +266,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     const int B = (int)target.numel();
     TORCH_CHECK(x.numel() == (int64_t)B * 784, "x must be [B,1,28,28]");
     float* g = nullptr;
-    if (grads.has_value()) { check_cuda_contig(*grads, "grads"); TORCH_CHECK(grads->scalar_type() == torch::kFloat32 && grads->numel() >= b2_convnet_npar()); g = grads->data_ptr<float>(); }
+    if (grads.has_value()) { check_cuda_contig(*grads, "grads"); TORCH_CHECK(grads->scalar_type() == torch::kFloat32 && grads->numel() >= b2_convnet_npar() + grad_stride); g = grads->data_ptr<float>(); }
     float* la = loss_acc.has_value() ? loss_acc->data_ptr<float>() : nullptr;
     float* lp = nullptr;
     if (out_logp.has_value()) { TORCH_CHECK(out_logp->numel() == (int64_t)B * 10 && out_logp->scalar_type() == torch::kFloat32); lp = out_logp->data_ptr<float>(); }
@@ -262,10 +276,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                   max_ctas, cur_stream()), "convnet_step launch");
+                                   max_ctas, grad_stride, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
-     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0);
+     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0);
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });
@@ -297,12 +311,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // ------------------------------------------------------------------ native step executor
   py::class_<ExecutorPy>(m, "StepExecutor")
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
-                    std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool,
-                    int, int, uint64_t, int64_t, double, double, double, int>(),
+                    std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
+                    int, int, uint64_t, int64_t, int64_t, double, double, double, int>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
-           py::arg("sig_ptrs"), py::arg("step"), py::arg("loss_acc"), py::arg("x_dev"), py::arg("y_dev"),
-           py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"), py::arg("sample_base"),
-           py::arg("lr"), py::arg("mu"), py::arg("p_drop"), py::arg("max_in_flight") = 3, py::keep_alive<1, 2>())
+           py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
+           py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
+           py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
+           py::arg("max_in_flight") = 3, py::keep_alive<1, 2>())
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
       .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
       .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });
@@ -317,5 +332,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("start_epoch", [](LoaderPy& l, int64_t e) { py::gil_scoped_release nogil; l.impl->start_epoch(e); })
       .def("next", &LoaderPy::next)
       .def("release", [](LoaderPy& l) { l.impl->release(); })
+      .def("block_bytes", [](LoaderPy& l) { return l.impl->block_bytes(); })
       .def("stop", [](LoaderPy& l) { py::gil_scoped_release nogil; l.impl->stop(); });
 }

@@ -14,7 +14,9 @@
 //   conv1.w 0 | conv1.b 252 | conv2.w 264 | conv2.b 5264 | fc1.w 5284 | fc1.b 21284 | fc2.w 21336 |
 //   fc2.b 21836 | total 21848
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cn {
 
@@ -22,18 +24,37 @@ constexpr int W1 = 0, B1 = 252, W2 = 264, B2 = 5264, W3 = 5284, B3 = 21284, W4 =
 constexpr int NPAR = 21848;
 constexpr int T = 512;              // 16 warps per sample: the phases are latency-bound, so more warps per CTA
 
-struct __align__(16) Smem {
-  float w1[252];
-  float b1[12];
+// The conv2 working set exists in two flavours that share one union:
+//   SIMT path : fp32 weights in two layouts + split-K partial sums + the zero-padded conv2-output gradient
+//   TC path   : bf16 UMMA operand tiles (K-major, 128B swizzle) for the two tcgen05 GEMMs of conv2
+//               forward  D[64 pos x 32 co]   = im2col(p1)[64 x 256] * W2[32 x 256]^T
+//               dgrad    D[64 pos x 256 k']  = dC[64 x 32 co]       * W2^T[256 x 32]^T      (k' = (ci/5)*128 + (ci%5)*25 + tap)
+struct SimtBufs {
   float w2f[250 * 20];      // [ci][ky][kx][co]          forward: 4 output channels per float4
   float w2b[500 * 16];      // [co][ky][kx][half][8]     backward-data: 5 input channels per (half)
+  float part[6 * 1440];     // conv2 partial sums [5][20][64] (5*1280 used) / dgrad partials [6][10][144]
+  float dc2pad[20 * 256];   // conv2-output gradient, zero padded [20][16][16]
+};
+struct TcBufs {
+  unsigned char Bw[4 * 4096];   // W2 as B operand (fwd): 4 K-blocks x [32 rows x 128 B]
+  unsigned char Bt[32768];      // W2^T as B operand (dgrad): [256 rows x 128 B] (K = co, 32 used)
+  unsigned char A[4 * 8192];    // im2col(p1) as A operand: 4 K-blocks x [64 rows x 128 B]; later dA staging [64][128] fp32
+  unsigned char Ad[8192];       // dC as A operand (dgrad) [64 rows x 128 B]; fwd: conv2 output staging [64][32] fp32
+};
+union Scratch {
+  SimtBufs simt;
+  TcBufs tc;
+};
+
+struct __align__(1024) Smem {
+  Scratch u;                // first member: 1024-byte aligned (UMMA SWIZZLE_128B tiles)
+  float w1[252];
+  float b1[12];
   float b2[20];
   float w4[500];
   float b4[12];
   float x[784];
   float p1[1440];           // relu(pool(conv1))  [10][12][12]
-  float part[6 * 1440];     // conv2 partial sums [5][20][64] (5*1280 used) / dgrad partials [6][10][144]
-  float dc2pad[20 * 256];   // conv2-output gradient, zero padded [20][16][16]
   float p2[320];            // relu(pool(drop(conv2)))  [20][4][4]
   float g2[320];            // gradient at the pooled conv2 argmax
   float2 g1[1440];          // (gradient at the pooled conv1 argmax, input offset of that position as int bits)
@@ -44,6 +65,9 @@ struct __align__(16) Smem {
   float m2[20];             // dropout2d channel scale
   float rnd[72];            // uniforms: [0,20) dropout2d, [20,70) dropout
   float g[NPAR];            // per-CTA gradient accumulators
+  unsigned long long mma_bar;   // mbarrier: tcgen05.commit -> "accumulator ready"
+  unsigned int tmem_slot;
+  short koff[256];          // im2col LUT: k=(ci,ky,kx) -> offset inside p1, -1 for the K padding
   unsigned char a1[1440];   // conv1 pool argmax (0..3)
   unsigned char a2[320];    // conv2 pool argmax (0..3)
   float loss_local;
@@ -72,12 +96,16 @@ struct Args {
   float inv_bsz;            // 1 / local batch (nll_loss mean)
   float p_drop;
   float mean, inv_std;      // uint8 normalisation
+  long long grad_stride;    // elements between the two gradient buckets (0: single bucket); bucket = step & 1
 };
 
+template <bool TC>
 __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x;
+  uint32_t mma_phase = 0;            // parity of the next "accumulator ready" wait (uniform across the CTA)
+  uint32_t tmem = 0;
   const float* __restrict__ P = a.params;
 
   // ---------------------------------------------------------------- P0: stage weights, zero accumulators
@@ -100,6 +128,15 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     if (tid < 250) s.w1[tid] = w1v;
     if (tid < 500) s.w4[tid] = w4v;
     if (tid < 10) s.b1[tid] = bv; else if (tid < 20) s.b4[tid - 10] = bv; else if (tid < 40) s.b2[tid - 20] = bv;
+    if (TC) {
+      // zero the bf16 operand tiles (row / K padding must be 0), build the im2col LUT, set up mbarrier + TMEM
+      uint4* z = reinterpret_cast<uint4*>(s.u.tc.Bw);
+      for (int i = tid; i < (16384 + 32768) / 16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (tid < 256) s.koff[tid] = tid < 250 ? (short)((tid / 25) * 144 + ((tid % 25) / 5) * 12 + (tid % 5)) : (short)-1;
+      if (tid == 0) { tc::mbar_init(reinterpret_cast<uint64_t*>(&s.mma_bar), 1); tc::mbar_fence_init(); }
+      if ((tid >> 5) == 1) tc::tmem_alloc<256>(&s.tmem_slot);
+      __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i4 = tid + k * T;
@@ -109,8 +146,15 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         for (int e = 0; e < 4; ++e) {             // conv2.weight [co][ci][ky][kx]
           const int i = i4 * 4 + e;
           const int co = i / 250, r = i % 250, ci = r / 25, kk = r % 25;
-          s.w2f[(ci * 25 + kk) * 20 + co] = w[e];
-          s.w2b[((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = w[e];
+          if (TC) {
+            const __nv_bfloat16 wb = __float2bfloat16(w[e]);
+            *reinterpret_cast<__nv_bfloat16*>(s.u.tc.Bw + (r >> 6) * 4096 + tc::sw128_offset(co, r & 63)) = wb;
+            const int n = (ci / 5) * 128 + (ci % 5) * 25 + kk;      // dgrad output column (ci groups on 128 boundaries)
+            *reinterpret_cast<__nv_bfloat16*>(s.u.tc.Bt + tc::sw128_offset(n, co)) = wb;
+          } else {
+            s.u.simt.w2f[(ci * 25 + kk) * 20 + co] = w[e];
+            s.u.simt.w2b[((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = w[e];
+          }
         }
       }
     }
@@ -118,7 +162,9 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   if (tid == 0) { s.loss_local = 0.f; s.correct_local = 0; }
   const unsigned long long step = a.step ? *a.step : 0ull;
   const float keep_scale = 1.f / (1.f - a.p_drop);
+  if (TC) { tc::fence_proxy_async(); tc::fence_before(); }
   __syncthreads();
+  if (TC) { tc::fence_after(); tmem = s.tmem_slot; }
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     // -------------------------------------------------------------- S0: input, RNG, clear scratch
@@ -142,8 +188,8 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       s.rnd[q * 4 + 0] = r.x * k; s.rnd[q * 4 + 1] = r.y * k;
       s.rnd[q * 4 + 2] = r.z * k; s.rnd[q * 4 + 3] = r.w * k;
     }
-    if (a.backward)
-      for (int i = tid; i < 20 * 256 / 4; i += T) reinterpret_cast<float4*>(s.dc2pad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TC && a.backward)
+      for (int i = tid; i < 20 * 256 / 4; i += T) reinterpret_cast<float4*>(s.u.simt.dc2pad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     // -------------------------------------------------------------- S1: conv1 -> maxpool2 -> relu
@@ -177,7 +223,59 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       s.m2[tid] = a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
     __syncthreads();
 
-    // -------------------------------------------------------------- S2: conv2 partial sums (K split 5)
+    // -------------------------------------------------------------- S2: conv2 (TC: im2col + tcgen05 GEMM | SIMT: K split 5)
+    if (TC) {
+      // im2col(p1) -> bf16 A operand, 2048 16-byte chunks (row = output position, 8 consecutive k per chunk)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int chunk = tid + m * T, r = chunk >> 5, c = chunk & 31;
+        const int base = (r >> 3) * 12 + (r & 7);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ko = s.koff[c * 8 + e];
+          f[e] = ko >= 0 ? s.p1[ko + base] : 0.f;
+        }
+        const uint4 pk = make_uint4(b2::pack_bf16x2(f[0], f[1]), b2::pack_bf16x2(f[2], f[3]), b2::pack_bf16x2(f[4], f[5]),
+                                    b2::pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(s.u.tc.A + (c >> 3) * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 7) ^ (r & 7)) & 7) << 4)) = pk;
+      }
+      tc::fence_proxy_async();
+      tc::fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after();
+        constexpr uint32_t idesc = tc::idesc_bf16(64, 32);
+        const uint32_t a0 = tc::smem_u32(s.u.tc.A), b0 = tc::smem_u32(s.u.tc.Bw);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_bf16(tmem, tc::smem_desc_sw128(a0 + kb * 8192 + k * 32), tc::smem_desc_sw128(b0 + kb * 4096 + k * 32),
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+        tc::commit(reinterpret_cast<uint64_t*>(&s.mma_bar));
+      }
+      tc::mbar_wait(reinterpret_cast<uint64_t*>(&s.mma_bar), mma_phase);
+      mma_phase ^= 1;
+      tc::fence_after();
+      if (tid < 128) {                            // UMMA_M = 64: rows 16q..16q+15 live in TMEM lanes 32q..32q+15
+        const int q = tid >> 5, lane = tid & 31;
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16), r);
+        tc::tmem_ld_wait();
+        if (lane < 16) {
+          const int row = q * 16 + lane;
+          float4* dst = reinterpret_cast<float4*>(s.u.tc.Ad) + row * 8;      // conv2 output staging [64][32] fp32
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            dst[c4 ^ (row & 7)] = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
+                                             __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+        }
+      }
+      tc::fence_before();
+      __syncthreads();
+    }
+    if (!TC) {
     if (tid < 400) {
       const int cell = tid & 15, cg = (tid >> 4) % 5, ks = tid / 80;
       const int py = cell >> 2, px = cell & 3;
@@ -198,7 +296,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
-            const float4 w = *reinterpret_cast<const float4*>(&s.w2f[((ci * 5 + ky) * 5 + kx) * 20 + cg * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&s.u.simt.w2f[((ci * 5 + ky) * 5 + kx) * 20 + cg * 4]);
             const float i00 = patch[ky][kx], i01 = patch[ky][kx + 1], i10 = patch[ky + 1][kx], i11 = patch[ky + 1][kx + 1];
             acc[0][0] = fmaf(w.x, i00, acc[0][0]); acc[0][1] = fmaf(w.y, i00, acc[0][1]);
             acc[0][2] = fmaf(w.z, i00, acc[0][2]); acc[0][3] = fmaf(w.w, i00, acc[0][3]);
@@ -213,19 +311,31 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       // part[ks][co][cell][pos]  (pos = dy*2+dx inside the pool window)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(&s.part[ks * 1440 + ((cg * 4 + c) * 16 + cell) * 4]) =
+        *reinterpret_cast<float4*>(&s.u.simt.part[ks * 1440 + ((cg * 4 + c) * 16 + cell) * 4]) =
             make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
     __syncthreads();
+    }
 
     // -------------------------------------------------------------- S2b: +bias, dropout2d, maxpool2, relu
     for (int o = tid; o < 320; o += T) {
       const int co = o >> 4;
-      float4 q = *reinterpret_cast<const float4*>(&s.part[o * 4]);
+      float4 q;
+      if (TC) {
+        const int cell = o & 15, p00 = (2 * (cell >> 2)) * 8 + 2 * (cell & 3);
+        const float* c2 = reinterpret_cast<const float*>(s.u.tc.Ad);
+        const int cb = co >> 2, cl = co & 3;
+        q.x = c2[(p00) * 32 + ((cb ^ ((p00) & 7)) << 2) + cl];
+        q.y = c2[(p00 + 1) * 32 + ((cb ^ ((p00 + 1) & 7)) << 2) + cl];
+        q.z = c2[(p00 + 8) * 32 + ((cb ^ ((p00 + 8) & 7)) << 2) + cl];
+        q.w = c2[(p00 + 9) * 32 + ((cb ^ ((p00 + 9) & 7)) << 2) + cl];
+      } else {
+        q = *reinterpret_cast<const float4*>(&s.u.simt.part[o * 4]);
 #pragma unroll
-      for (int ks = 1; ks < 5; ++ks) {
-        const float4 t = *reinterpret_cast<const float4*>(&s.part[ks * 1440 + o * 4]);
-        q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+        for (int ks = 1; ks < 5; ++ks) {
+          const float4 t = *reinterpret_cast<const float4*>(&s.u.simt.part[ks * 1440 + o * 4]);
+          q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+        }
       }
       const float bias = s.b2[co], sc = s.m2[co];
       const float v0 = (q.x + bias) * sc, v1 = (q.y + bias) * sc, v2 = (q.z + bias) * sc, v3 = (q.w + bias) * sc;
@@ -334,8 +444,10 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         const int co = o >> 4, cell = o & 15, arg = s.a2[o];
         const float gv = s.p2[o] > 0.f ? d * s.m2[co] : 0.f;
         s.g2[o] = gv;
-        const int y = 2 * (cell >> 2) + (arg >> 1), x = 2 * (cell & 3) + (arg & 1);
-        s.dc2pad[co * 256 + (y + 4) * 16 + (x + 4)] = gv;
+        if (!TC) {
+          const int y = 2 * (cell >> 2) + (arg >> 1), x = 2 * (cell & 3) + (arg & 1);
+          s.u.simt.dc2pad[co * 256 + (y + 4) * 16 + (x + 4)] = gv;
+        }
       }
     }
     __syncthreads();
@@ -366,7 +478,83 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
       s.g[B2 + co] += d;
     }
-    // -------------------------------------------------------------- S7b: conv2 data gradient (dense, K split 6)
+    // -------------------------------------------------------------- S7b/S8a: conv2 data gradient -> gradient at conv1's pooled argmax
+    if (TC) {
+      // dC[64 pos][co] (one non-zero per pool window and channel) as the bf16 A operand; K = co (32 of the 64 columns used)
+      if (tid < 256) {
+        const int r = tid >> 2, c8 = tid & 3, oy = r >> 3, ox = r & 7;
+        const int cell = (oy >> 1) * 4 + (ox >> 1), sub = (oy & 1) * 2 + (ox & 1);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co = c8 * 8 + e;
+          f[e] = (co < 20 && s.a2[co * 16 + cell] == sub) ? s.g2[co * 16 + cell] : 0.f;
+        }
+        const uint4 pk = make_uint4(b2::pack_bf16x2(f[0], f[1]), b2::pack_bf16x2(f[2], f[3]), b2::pack_bf16x2(f[4], f[5]),
+                                    b2::pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(s.u.tc.Ad + (r >> 3) * 1024 + (r & 7) * 128 + (((c8 ^ (r & 7)) & 7) << 4)) = pk;
+      }
+      tc::fence_proxy_async();
+      tc::fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after();
+        constexpr uint32_t idesc = tc::idesc_bf16(64, 256);
+        const uint32_t a0 = tc::smem_u32(s.u.tc.Ad), b0 = tc::smem_u32(s.u.tc.Bt);
+        tc::umma_bf16(tmem, tc::smem_desc_sw128(a0), tc::smem_desc_sw128(b0), idesc, 0u);
+        tc::umma_bf16(tmem, tc::smem_desc_sw128(a0 + 32), tc::smem_desc_sw128(b0 + 32), idesc, 1u);
+        tc::commit(reinterpret_cast<uint64_t*>(&s.mma_bar));
+      }
+      tc::mbar_wait(reinterpret_cast<uint64_t*>(&s.mma_bar), mma_phase);
+      mma_phase ^= 1;
+      tc::fence_after();
+      float* stage = reinterpret_cast<float*>(s.u.tc.A);      // [64 rows][128 cols] fp32, float4 index XOR-swizzled by row
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {                  // input channels 5*half .. 5*half+4  <->  TMEM columns 128*half ..
+        if (tid < 128) {
+          const int q = tid >> 5, lane = tid & 31, row = q * 16 + (lane & 15);
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128 + cc * 32), r);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+              float4* dst = reinterpret_cast<float4*>(stage) + row * 32;
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                dst[(cc * 8 + c4) ^ (row & 31)] = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
+                                                              __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+            }
+          }
+        }
+        tc::fence_before();
+        __syncthreads();
+        // col2im gather: dp1[ci][y][x] = sum_{ky,kx} dA[(y-ky, x-kx)][ci, ky, kx], fused with relu'/pool routing of conv1
+        for (int o5 = tid; o5 < 720; o5 += T) {
+          const int cil = o5 / 144, rem = o5 - cil * 144, y = rem / 12, x = rem - y * 12;
+          float d = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const int oy = y - ky;
+            if ((unsigned)oy < 8u) {
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) {
+                const int ox = x - kx;
+                if ((unsigned)ox < 8u) {
+                  const int row = oy * 8 + ox, j = cil * 25 + ky * 5 + kx;
+                  d += stage[row * 128 + ((((j >> 2) ^ (row & 31)) & 31) << 2) + (j & 3)];
+                }
+              }
+            }
+          }
+          const int o = (half * 5 + cil) * 144 + rem, arg = s.a1[o];
+          const int off = (2 * y + (arg >> 1)) * 28 + 2 * x + (arg & 1);
+          s.g1[o] = make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off));
+        }
+        __syncthreads();
+      }
+    }
+    if (!TC) {
     if (tid < 432) {
       const int tile = tid % 36, half = (tid / 36) & 1, ks = tid / 72;
       const int y0 = 2 * (tile / 6), x0 = 2 * (tile % 6);
@@ -379,7 +567,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       for (int co = co0; co < co1; ++co) {
         if (s.m2[co] == 0.f) continue;            // channel dropped by Dropout2d: gradient plane is zero
         float patch[6][6];
-        const float* src = &s.dc2pad[co * 256 + y0 * 16 + x0];
+        const float* src = &s.u.simt.dc2pad[co * 256 + y0 * 16 + x0];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -388,7 +576,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
-            const float* wp = &s.w2b[((co * 25 + ky * 5 + kx) * 2 + half) * 8];
+            const float* wp = &s.u.simt.w2b[((co * 25 + ky * 5 + kx) * 2 + half) * 8];
             const float4 w = *reinterpret_cast<const float4*>(wp);
             const float w4 = wp[4];
             const float d00 = patch[4 - ky][4 - kx], d01 = patch[4 - ky][5 - kx];
@@ -405,7 +593,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       }
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
-        float* dst = &s.part[ks * 1440 + (half * 5 + c) * 144 + y0 * 12 + x0];
+        float* dst = &s.u.simt.part[ks * 1440 + (half * 5 + c) * 144 + y0 * 12 + x0];
         dst[0] = acc[0][c]; dst[1] = acc[1][c]; dst[12] = acc[2][c]; dst[13] = acc[3][c];
       }
     }
@@ -415,12 +603,13 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     for (int o = tid; o < 1440; o += T) {
       float d = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < 6; ++ks) d += s.part[ks * 1440 + o];
+      for (int ks = 0; ks < 6; ++ks) d += s.u.simt.part[ks * 1440 + o];
       const int cell = o % 144, arg = s.a1[o];
       const int off = (2 * (cell / 12) + (arg >> 1)) * 28 + 2 * (cell % 12) + (arg & 1);
       s.g1[o] = make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off));
     }
     __syncthreads();
+    }
 
     // -------------------------------------------------------------- S8b: conv1 weight/bias gradient (sparse)
     {
@@ -451,14 +640,20 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 
   // ------------------------------------------------------------------ flush
   if (a.backward && blockIdx.x < a.B) {
+    float* gdst = a.grads + (size_t)(step & 1ull) * (size_t)a.grad_stride;   // double-buffered buckets: see sgd.cu
     for (int v = tid; v < NPAR / 4; v += T) {
       const float4 q = *reinterpret_cast<const float4*>(&s.g[v * 4]);
-      red_add_v4(a.grads + v * 4, q.x, q.y, q.z, q.w);
+      red_add_v4(gdst + v * 4, q.x, q.y, q.z, q.w);
     }
   }
   if (tid == 0 && a.loss_acc != nullptr && blockIdx.x < a.B) {
     atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
     atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+  }
+  if (TC) {
+    tc::fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 1) { tc::fence_after(); tc::tmem_dealloc<256>(tmem); }
   }
 }
 
@@ -466,17 +661,29 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 
 extern "C" {
 
-size_t b2_convnet_smem_bytes() { return sizeof(cn::Smem); }
+size_t b2_convnet_smem_bytes() { return sizeof(cn::Smem) + 1024; }
 int b2_convnet_npar() { return cn::NPAR; }
+
+static int g_convnet_tc = -1;      // -1: read B200DIST_CONVNET_TC on first use
+void b2_convnet_set_tc(int on) { g_convnet_tc = on ? 1 : 0; }
+int b2_convnet_get_tc() {
+  if (g_convnet_tc < 0) {
+    const char* e = getenv("B200DIST_CONVNET_TC");
+    g_convnet_tc = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_convnet_tc;
+}
 
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, cudaStream_t stream) {
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem = sizeof(cn::Smem);
+  const size_t smem = sizeof(cn::Smem) + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(cn::convnet_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cn::convnet_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(cn::convnet_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -484,11 +691,12 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   a.params = params; a.grads = grads; a.x = x; a.target = target; a.loss_acc = loss_acc; a.out_logp = out_logp;
   a.mask_out = mask_out; a.step = step; a.seed = seed; a.sample_base = sample_base; a.B = B; a.x_u8 = x_u8;
   a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
-  a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f;
+  a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride;
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  cn::convnet_step_kernel<<<grid, cn::T, smem, stream>>>(a);
+  if (b2_convnet_get_tc()) cn::convnet_step_kernel<true><<<grid, cn::T, smem, stream>>>(a);
+  else cn::convnet_step_kernel<false><<<grid, cn::T, smem, stream>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -14,16 +14,16 @@ namespace b2 {
 struct StepConfig {
   float* params;
   float* momentum;
-  float* grads_local;                // this rank's gradient bucket
+  float* grads_local;                // this rank's gradient bucket(s)
   void* grad_ptrs[8];                // every rank's bucket (symmetric mapping), [0] only when world == 1
   uint32_t* sig_ptrs[8];
   unsigned long long* step_counter;
+  unsigned int* done_counter;
   float* loss_acc;                   // [2]
-  void* x_dev;                       // [B,1,28,28] fp32 or uint8
-  long long* y_dev;                  // [B]
+  unsigned char* in_dev[2];          // double-buffered device input blocks, same layout as a loader slot: [x | pad | y]
   int B, x_u8, training, rank, world;
   unsigned long long seed;
-  long long sample_base;
+  long long sample_base, grad_stride;
   float lr, mu, p_drop;
 };
 
@@ -41,18 +41,20 @@ class StepExecutor {
 
  private:
   struct Slot {
-    cudaGraphExec_t exec = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;      // loss of the step fed from this slot has landed in loss_pin
     float* loss_pin = nullptr;
   };
-  bool capture(int slot);
+  bool capture(int parity);
   void retire_oldest();
   StepConfig cfg_;
   NativeLoader* loader_;
   int max_in_flight_;
-  cudaStream_t stream_ = nullptr;
+  cudaStream_t copy_ = nullptr, compute_ = nullptr, d2h_ = nullptr;
+  cudaGraphExec_t exec_[2] = {nullptr, nullptr};     // the two kernels, reading in_dev[parity]
+  cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr};
   std::vector<Slot> slots_;
   std::deque<int> in_flight_;
+  int64_t issued_ = 0;
   double last_loss_ = 0.0;
   std::string err_;
 };

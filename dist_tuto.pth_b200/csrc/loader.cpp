@@ -26,18 +26,19 @@ NativeLoader::NativeLoader(const uint8_t* images, const int64_t* labels, int64_t
   if (batch_ <= 0) throw std::invalid_argument("batch must be positive");
   const size_t xbytes = (size_t)batch_ * item_ * (raw_ ? 1 : sizeof(float));
   const size_t ybytes = (size_t)batch_ * sizeof(int64_t);
+  y_offset_ = (xbytes + 255) / 256 * 256;          // one block per slot: [x | pad | y] -> ONE H2D copy per step
+  block_bytes_ = y_offset_ + ybytes;
   slots_.resize(nbuf_);
   for (auto& s : slots_) {
     if (pinned_) {
-      if (cudaHostAlloc(&s.x, xbytes, cudaHostAllocDefault) != cudaSuccess ||
-          cudaHostAlloc((void**)&s.y, ybytes, cudaHostAllocDefault) != cudaSuccess) {
+      if (cudaHostAlloc(&s.x, block_bytes_, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         throw std::runtime_error("cudaHostAlloc failed");
       }
     } else {
-      s.x = ::operator new(xbytes);
-      s.y = static_cast<int64_t*>(::operator new(ybytes));
+      s.x = ::operator new(block_bytes_);
     }
+    s.y = reinterpret_cast<int64_t*>(static_cast<unsigned char*>(s.x) + y_offset_);
   }
   order_ = index_;
 }
@@ -45,8 +46,8 @@ NativeLoader::NativeLoader(const uint8_t* images, const int64_t* labels, int64_t
 NativeLoader::~NativeLoader() {
   stop();
   for (auto& s : slots_) {
-    if (pinned_) { cudaFreeHost(s.x); cudaFreeHost(s.y); }
-    else { ::operator delete(s.x); ::operator delete(s.y); }
+    if (pinned_) cudaFreeHost(s.x);
+    else ::operator delete(s.x);
   }
 }
 

@@ -26,6 +26,8 @@ class NativeLoader {
   void stop();
   const Slot& slot(int i) const { return slots_[i]; }
   int num_slots() const { return nbuf_; }
+  size_t y_offset() const { return y_offset_; }
+  size_t block_bytes() const { return block_bytes_; }
   int64_t batch() const { return batch_; }
   int64_t item() const { return item_; }
   bool raw() const { return raw_; }
@@ -44,6 +46,7 @@ class NativeLoader {
   float mean_, inv_std_;
   uint64_t seed_;
   bool pinned_;
+  size_t y_offset_ = 0, block_bytes_ = 0;
   std::vector<Slot> slots_;
   std::thread worker_;
   std::mutex mu_;

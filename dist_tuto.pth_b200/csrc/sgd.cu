@@ -20,10 +20,12 @@ struct SgdArgs {
   float* params;
   float* momentum;
   unsigned long long* step;  // incremented once per call (may be null)
+  unsigned int* done_counter; // block-completion counter (device scratch, zero between calls)
   size_t n_vec;              // float4 vectors
   float lr, mu, scale;
   int rank, world;
   int zero_grads;
+  long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
 };
 
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
@@ -34,6 +36,12 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
     block_barrier_all_ranks(a.sig, rank, world, ++epoch);           // all gradient buckets are complete
   }
   const size_t stride = (size_t)gridDim.x * kSgdThreads;
+  // Double-buffered buckets remove the second barrier: once every rank has arrived at THIS step's barrier it has
+  // finished reading last step's bucket, so that one can be zeroed right away for the step after this one.
+  const bool dbuf = a.grad_stride > 0;
+  const size_t par = (dbuf && a.step != nullptr) ? (size_t)(*a.step & 1ull) : 0;
+  const size_t cur_off = par * (size_t)a.grad_stride * sizeof(float);
+  const size_t oth_off = (par ^ 1) * (size_t)a.grad_stride * sizeof(float);
   // block-uniform trip count (barrier inside the loop)
   for (size_t base = (size_t)blockIdx.x * kSgdThreads; base < a.n_vec; base += stride) {
     const size_t v = base + threadIdx.x;
@@ -43,7 +51,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
       uint4 raw[B2_MAX_RANKS];
 #pragma unroll
       for (int r = 0; r < B2_MAX_RANKS; ++r)
-        if (r < world) raw[r] = ld_cg_v4(reinterpret_cast<const uint4*>(a.grads.p[r]) + v);
+        if (r < world) raw[r] = ld_cg_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.grads.p[r]) + cur_off) + v);
 #pragma unroll
       for (int r = 0; r < B2_MAX_RANKS; ++r)
         if (r < world) {
@@ -59,12 +67,24 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
       reinterpret_cast<float4*>(a.params)[v] = p;
     }
     if (a.zero_grads) {
-      if (world > 1) block_barrier_all_ranks(a.sig, rank, world, ++epoch);   // peers are done reading this pass
-      if (ok) st_cg_v4(reinterpret_cast<uint4*>(a.grads.p[rank]) + v, make_uint4(0u, 0u, 0u, 0u));
+      if (dbuf) {
+        if (ok) st_cg_v4(reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.grads.p[rank]) + oth_off) + v, make_uint4(0u, 0u, 0u, 0u));
+      } else {
+        if (world > 1) block_barrier_all_ranks(a.sig, rank, world, ++epoch);   // peers are done reading this pass
+        if (ok) st_cg_v4(reinterpret_cast<uint4*>(a.grads.p[rank]) + v, make_uint4(0u, 0u, 0u, 0u));
+      }
     }
   }
   if (world > 1 && threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
-  if (a.step != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.step += 1ull;
+  // every block read `*a.step` at its start; the bump must not overtake a late block -> last block to finish bumps it
+  if (a.step != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(a.done_counter, 1u);
+      if (done == gridDim.x - 1) { *a.done_counter = 0u; __threadfence(); *a.step += 1ull; }
+    }
+  }
 }
 
 // Plain flat momentum SGD (generic models: gradients already averaged in `grad`)
@@ -100,11 +120,12 @@ extern "C" {
 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, cudaStream_t stream) {
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream) {
   b2::SgdArgs a;
   a.grads = *grads; a.sig = *sig; a.params = params; a.momentum = momentum; a.step = step;
   a.n_vec = n_elems / 4; a.lr = lr; a.mu = mu; a.scale = scale; a.rank = rank; a.world = world;
-  a.zero_grads = zero_grads;
+  a.zero_grads = zero_grads; a.grad_stride = grad_stride; a.done_counter = done_counter;
+  if (step != nullptr && done_counter == nullptr) return (int)cudaErrorInvalidValue;
   size_t blocks = (a.n_vec + b2::kSgdThreads - 1) / b2::kSgdThreads;
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;

@@ -117,13 +117,18 @@ class FusedTrainer:
         if self.world > 1:
             from ..parallel import symm
             self.symm = symm.lookup_world(comm._g(group)) or symm.init_world(comm._g(group))
-            self.grad_handle = self.symm.alloc(NPAR_ALLOC, torch.float32)
+            self.grad_handle = self.symm.alloc(2 * NPAR_ALLOC, torch.float32)
             self.grads = self.grad_handle.local
+            self.grads.zero_()
             self._grad_ptrs, self._sig_ptrs = self.grad_handle.ptrs, self.grad_handle.sig_ptrs
         else:
-            self.grads = torch.zeros(NPAR_ALLOC, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros(2 * NPAR_ALLOC, dtype=torch.float32, device=self.device)
             self._grad_ptrs, self._sig_ptrs = [self.grads.data_ptr()], [0]
+        # two gradient buckets, selected by (step & 1) inside the kernels: the all-reduce kernel re-zeroes the bucket
+        # of the previous step, which needs no second cross-GPU barrier (see csrc/sgd.cu)
+        self.grad_stride = NPAR_ALLOC
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.done_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=self.device)   # [sum of batch-mean nll, #correct]
         xdt = torch.uint8 if raw_uint8 else torch.float32
         self.x_dev = torch.zeros(self.bsz, 1, 28, 28, dtype=xdt, device=self.device)
@@ -150,9 +155,10 @@ class FusedTrainer:
     # ------------------------------------------------------------------ kernels
     def _kernels(self, x, y, B):
         self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
-                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0)
+                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
-                             self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True)
+                             self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
+                             self.done_counter)
 
     def _warm(self):
         # forward-only launch: sets the kernel's dynamic-smem attribute outside of graph capture
@@ -259,10 +265,15 @@ class FusedTrainer:
         self.stream.synchronize()
         ex = self._executors.get(id(loader))
         if ex is None or ex[1] != self.training:
+            if loader.batch_size != self.bsz:
+                raise ValueError("loader batch size != trainer batch size")
+            block = (int(loader._l.block_bytes()) + 255) // 256 * 256
+            in_dev = torch.zeros(2 * block, dtype=torch.uint8, device=self.device)
             ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
-                                      self.step_counter, self.loss_acc, self.x_dev, self.y_dev, self.training, self.rank,
-                                      self.world, self.seed, self.rank * self.bsz, self.lr, self.mu, self.p_drop,
-                                      max(1, loader.num_buffers - 2)), self.training)
+                                      self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
+                                      self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
+                                      self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2)),
+                  self.training)
             self._executors[id(loader)] = ex
         if new_epoch:
             loader.begin_epoch()

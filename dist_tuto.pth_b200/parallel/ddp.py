@@ -68,8 +68,30 @@ class GradBucket:
             self.flat.zero_()
         else:
             self.flat = torch.zeros(n, dtype=self.dtype, device=dev)
-        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        # a view has the parameter's own strides (e.g. channels_last conv weights), so autograd accumulates
+        # straight into the bucket without a layout-converting copy
+        self.views = []
+        for o, p in zip(self.offsets, self.params):
+            seg = self.flat[o:o + p.numel()]
+            dense = p.is_contiguous() or p.numel() == 0
+            if not dense and torch._debug_has_internal_overlap(p) == 0 and self._dense_strides(p):
+                self.views.append(seg.as_strided(p.shape, p.stride()))
+            else:
+                self.views.append(seg.view(p.shape))
         self.attach()
+
+    @staticmethod
+    def _dense_strides(p) -> bool:
+        """True when ``p`` covers exactly numel() elements under some dimension permutation."""
+        dims = sorted(range(p.dim()), key=lambda d: (p.stride(d), p.size(d)))
+        expect = 1
+        for d in dims:
+            if p.size(d) == 1:
+                continue
+            if p.stride(d) != expect:
+                return False
+            expect *= p.size(d)
+        return expect == p.numel()
 
     def attach(self) -> None:
         """(Re)point every ``p.grad`` at its view (keeps current values)."""
@@ -84,13 +106,13 @@ class GradBucket:
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
 
-    def all_reduce_average_(self) -> None:
-        """flat <- mean over ranks (in place)."""
+    def all_reduce_average_(self, max_blocks: Optional[int] = None) -> None:
+        """flat <- mean over ranks (in place).  ``max_blocks`` caps the comm kernel's CTAs (overlap mode)."""
         size = comm.get_world_size(self.group)
         if size == 1:
             return
         if self.world is not None:
-            self.world.all_reduce_(self.flat, scale=1.0 / size, handle=self.symm_handle)
+            self.world.all_reduce_(self.flat, scale=1.0 / size, handle=self.symm_handle, max_blocks=max_blocks)
         else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=comm._g(self.group))
             self.flat.div_(size)
@@ -175,7 +197,8 @@ class DistributedDataParallel(nn.Module):
     ``average_gradients(model)`` or ``optimizer`` glue) joins the streams."""
 
     def __init__(self, module: nn.Module, group=None, bucket_cap_bytes: int = 8 << 20,
-                 overlap: bool = True, broadcast: bool = True, grad_dtype: Optional[torch.dtype] = None):
+                 overlap: bool = True, broadcast: bool = True, grad_dtype: Optional[torch.dtype] = None,
+                 comm_blocks: int = 32):
         super().__init__()
         self.module = module
         self.group = group
@@ -185,10 +208,13 @@ class DistributedDataParallel(nn.Module):
             raise ValueError("module has no trainable parameters")
         self.device = params[0].device
         self.overlap = bool(overlap) and self.device.type == "cuda" and self.world_size > 1
+        # while backward kernels are running the comm kernel gets a slice of the SMs, not all of them
+        self.comm_blocks = comm_blocks if self.overlap else None
         if broadcast:
             broadcast_parameters(module, 0, group)
         self._buckets: List[_Bucket] = []
         self._bucket_of = {}
+        self._view_of = {}
         cur, cur_bytes = [], 0
         for p in reversed(params):
             nbytes = p.numel() * (torch.empty((), dtype=grad_dtype or p.dtype).element_size())
@@ -210,8 +236,9 @@ class DistributedDataParallel(nn.Module):
     def _add_bucket(self, params, grad_dtype):
         gb = GradBucket(params, group=self.group, dtype=grad_dtype)
         b = _Bucket(gb)
-        for p in gb.params:
+        for p, v in zip(gb.params, gb.views):
             self._bucket_of[p] = b
+            self._view_of[p] = v
         self._buckets.append(b)
 
     @property
@@ -242,14 +269,13 @@ class DistributedDataParallel(nn.Module):
             ev.record(cur)
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                b.gb.all_reduce_average_()
+                b.gb.all_reduce_average_(self.comm_blocks)
         else:
             b.gb.all_reduce_average_()
 
     def _on_grad(self, p: nn.Parameter):
         b = self._bucket_of[p]
-        i = next(k for k, q in enumerate(b.gb.params) if q is p)
-        v = b.gb.views[i]
+        v = self._view_of[p]
         if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
             v.copy_(p.grad)       # optimizer.zero_grad(set_to_none=True) detached the view
             p.grad = v

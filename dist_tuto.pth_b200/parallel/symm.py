@@ -117,7 +117,9 @@ class SymmWorld:
         self._handles: List[SymmHandle] = []
         self._staging: Dict[torch.dtype, SymmHandle] = {}
         self._lock = threading.Lock()
-        self.max_blocks = _env_int("B200DIST_AR_BLOCKS", 0)
+        # every CTA of a comm kernel spins on peer flags, so the grid never exceeds what is co-resident (1 CTA / SM)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.max_blocks = _env_int("B200DIST_AR_BLOCKS", 0) or min(sms, 148)
         # size thresholds (wire bytes); overridable, see bench/allreduce_sweep.py for the measured table
         self.oneshot_max = _env_int("B200DIST_ONESHOT_MAX", 512 << 10)
         self.nvls_min = _env_int("B200DIST_NVLS_MIN", 256 << 10)
@@ -244,7 +246,8 @@ class SymmWorld:
             return 0
         return 2 if self.multicast else 1
 
-    def _launch(self, hd: SymmHandle, bf16: bool, n_vec: int, scale: float, src, dst, variant: Optional[int]):
+    def _launch(self, hd: SymmHandle, bf16: bool, n_vec: int, scale: float, src, dst, variant: Optional[int],
+                max_blocks: Optional[int] = None):
         wire_bytes = n_vec * 16
         v = self.pick_variant(wire_bytes) if variant is None else variant
         if v == 2 and not hd.mc_ptr:
@@ -252,11 +255,12 @@ class SymmWorld:
         if v != 0:
             n_vec = (n_vec + self.world - 1) // self.world * self.world
         self.C.allreduce(v, bf16, hd.ptrs, hd.sig_ptrs, hd.mc_ptr, src, dst, n_vec, float(scale), self.rank,
-                         self.world, self.max_blocks)
+                         self.world, self.max_blocks if max_blocks is None else max_blocks)
         return v
 
     def all_reduce_(self, t: torch.Tensor, scale: float = 1.0, handle: Optional[SymmHandle] = None,
-                    variant: Optional[int] = None, wire: Optional[torch.dtype] = None) -> torch.Tensor:
+                    variant: Optional[int] = None, wire: Optional[torch.dtype] = None,
+                    max_blocks: Optional[int] = None) -> torch.Tensor:
         """In-place ``t <- scale * sum_ranks t`` with the fused peer-memory kernels.
 
         ``handle`` given and ``t`` aliasing its data  -> zero-copy symmetric path;
@@ -274,7 +278,7 @@ class SymmWorld:
                 t.data_ptr() + t.numel() * es <= handle.ptrs[self.rank] + handle.nbytes and \
                 t.data_ptr() == handle.ptrs[self.rank] and (wire is None or wire == t.dtype):
             nbytes = (t.numel() * es + 15) // 16 * 16
-            self._launch(handle, t.dtype == torch.bfloat16, nbytes // 16, scale, None, None, variant)
+            self._launch(handle, t.dtype == torch.bfloat16, nbytes // 16, scale, None, None, variant, max_blocks)
             return t
         wire_dt = wire or t.dtype
         if wire_dt not in _DTYPES or (wire_dt == torch.float32 and t.dtype == torch.bfloat16):
@@ -284,12 +288,12 @@ class SymmWorld:
         st = self._staging_for(wire_dt, wire_bytes)
         flat = t.view(-1)
         if wire_bytes % (16 * self.world) == 0 and t.data_ptr() % 16 == 0:
-            self._launch(st, wire_dt == torch.bfloat16, wire_bytes // 16, scale, flat, flat, variant)
+            self._launch(st, wire_dt == torch.bfloat16, wire_bytes // 16, scale, flat, flat, variant, max_blocks)
         else:  # ragged size: torch copies around an in-place symmetric all-reduce
             buf = st.view(wire_dt, (wire_bytes + 15) // 16 * 16 // wes + 64 * 8)
             buf[:flat.numel()].copy_(flat)
             buf[flat.numel():].zero_()
-            self._launch(st, wire_dt == torch.bfloat16, (wire_bytes + 15) // 16, scale, None, None, variant)
+            self._launch(st, wire_dt == torch.bfloat16, (wire_bytes + 15) // 16, scale, None, None, variant, max_blocks)
             flat.copy_(buf[:flat.numel()])
         return t
 

@@ -215,3 +215,52 @@ def test_native_executor_matches_python_loop(dev):
     assert res[0][2] == res[1][2] == 16
     assert abs(res[0][1] - res[1][1]) < 1e-3 * abs(res[1][1])
     assert torch.allclose(res[0][0], res[1][0], atol=1e-5, rtol=1e-4)
+
+
+@pytest.fixture
+def tc_mode():
+    from dist_tuto.pth_b200.ops import _ext
+    C = _ext.C()
+    prev = C.convnet_get_tc()
+    C.convnet_set_tc(True)
+    yield
+    C.convnet_set_tc(prev)
+
+
+@pytest.mark.parametrize("B", [1, 16, 128, 200])
+def test_convnet_tcgen05_path_matches_fp64_oracle(dev, tc_mode, B):
+    """conv2 forward + data-gradient on the tensor cores (bf16 operands, fp32 accumulate in TMEM)."""
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, convnet_forward, pack_params, unpack_params
+    net = _net(dev, seed=3).eval()
+    x, y = _batch(dev, B, seed=5)
+    flat = pack_params(net)
+    out = convnet_forward(flat, x)
+    ref_out = net(x)
+    assert torch.allclose(out, ref_out, atol=3e-2, rtol=3e-2), float((out - ref_out).abs().max())
+    loss, grads = convnet_loss_and_grads(flat, x, y, training=False)
+    net64 = net.double()
+    ref_loss = F.nll_loss(net64(x.double()), y)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-2 * max(1.0, abs(float(ref_loss)))
+    views = unpack_params(grads)
+    errs = {}
+    for name, p in net64.named_parameters():
+        scale = p.grad.abs().max().clamp_min(1e-9)
+        errs[name] = float((views[name].double() - p.grad).abs().max() / scale)
+    assert max(errs.values()) < 5e-2, errs
+    # the two paths must agree with each other much more tightly than bf16 noise on everything downstream of conv2
+    assert errs["fc2.weight"] < 3e-2 and errs["conv1.weight"] < 5e-2
+
+
+def test_convnet_tcgen05_training_with_dropout(dev, tc_mode):
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    tr = FusedTrainer(64, lr=0.05, seed=1, device=dev, p_drop=0.5)
+    g = torch.Generator().manual_seed(0)
+    losses = []
+    xs = torch.randn(64, 1, 28, 28, generator=g)
+    ys = torch.randint(0, 10, (64,), generator=g)
+    for i in range(30):                                   # overfit one batch: loss must fall
+        tr.step(xs.pin_memory(), ys.pin_memory())
+        if i in (0, 29):
+            losses.append(tr.pop_loss_sum())
+    assert losses[1] < losses[0], losses
