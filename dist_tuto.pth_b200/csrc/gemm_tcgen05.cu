@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -222,6 +223,165 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 
+// ------------------------------------------------------------------------------------------ persistent 128x256 kernel
+// Large GEMMs: one CTA per SM loops over output tiles; 128x256 tiles halve the operand bytes per FLOP relative to
+// 128x128 (the L2->SM path is the bound at this size), and TWO TMEM accumulators (2 x 256 columns) let the epilogue of
+// tile i overlap the mainloop of tile i+1.
+constexpr int PBN = 256, PSTAGES = 4;
+struct PSmem {
+  alignas(1024) uint8_t a[PSTAGES][BM * BK * 2];
+  alignas(1024) uint8_t b[PSTAGES][PBN * BK * 2];
+  alignas(8) uint64_t full[PSTAGES];
+  alignas(8) uint64_t empty[PSTAGES];
+  alignas(8) uint64_t tmem_full[2];
+  alignas(8) uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            void* __restrict__ c, const float* __restrict__ bias, int M, int N, int K, int relu, int out_bf16) {
+  extern __shared__ uint8_t smem_raw[];
+  PSmem& s = *reinterpret_cast<PSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (M + BM - 1) / BM, nt = (N + PBN - 1) / PBN, tiles = mt * nt;
+  const int num_kb = (K + BK - 1) / BK;
+  constexpr uint32_t kStageBytes = (BM + PBN) * BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int i = 0; i < PSTAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem0 = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                                          // global k-block counter -> stage / phase
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t % mt) * BM, n0 = (t / mt) * PBN;      // consecutive CTAs share the B (N) panel
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % PSTAGES;
+          mbar_wait(&s.empty[st], ((it / PSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&s.full[st], kStageBytes);
+          tma_load_2d(s.a[st], &map_a, &s.full[st], kb * BK, m0);
+          tma_load_2d(s.b[st], &map_b, &s.full[st], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, PBN);
+      uint32_t it = 0, li = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++li) {
+        const uint32_t acc = li & 1;
+        mbar_wait(&s.tmem_empty[acc], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % PSTAGES;
+          mbar_wait(&s.full[st], (it / PSTAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem0 + acc * PBN, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          tcgen05_commit(&s.empty[st]);
+        }
+        tcgen05_commit(&s.tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    uint32_t li = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++li) {
+      const uint32_t acc = li & 1;
+      const int m0 = (t % mt) * BM, n0 = (t / mt) * PBN;
+      mbar_wait(&s.tmem_full[acc], (li >> 1) & 1);
+      tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < PBN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem0 + acc * PBN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int colb = n0 + c0;
+        if (row < M && colb < N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]);
+            if (bias != nullptr && colb + i < N) x += __ldg(bias + colb + i);
+            if (relu) x = fmaxf(x, 0.f);
+            v[i] = x;
+          }
+          if (out_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c) + (size_t)row * N + colb;
+            if (colb + 32 <= N && (N % 8) == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 pk;
+                __nv_bfloat162 t2;
+                t2 = __floats2bfloat162_rn(v[8 * g], v[8 * g + 1]);     pk.x = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
+                reinterpret_cast<uint4*>(dst)[g] = pk;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (colb + i < N) dst[i] = __float2bfloat16(v[i]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(c) + (size_t)row * N + colb;
+            if (colb + 32 <= N && (N % 4) == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) reinterpret_cast<float4*>(dst)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (colb + i < N) dst[i] = v[i];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);            // this warp's quarter of the accumulator is drained
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ M=64 layout probe
 // D[64 x 32] = A[64 x 64] * B[32 x 64]^T with a UMMA_M = 64 instruction; the kernel zero-fills TMEM first and then
 // dumps all 128 TMEM lanes x 32 columns, so the host can read off which lane holds which accumulator row.
@@ -341,6 +501,28 @@ int launch(const void* a, const void* b, void* c, const float* bias, int M, int 
   return 0;
 }
 
+int launch_persistent(const void* a, const void* b, void* c, const float* bias, int M, int N, int K, int relu, int out_bf16,
+                      cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, a, M, K, BM) || !make_map(&mb, b, N, K, PBN)) return -1;
+  const size_t smem = sizeof(PSmem) + 1024;
+  static int sms = 0;
+  if (sms == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -2; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + PBN - 1) / PBN);
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_bf16_persistent_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, c, bias, M, N, K, relu, out_bf16);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err = std::string("launch: ") + cudaGetErrorString(e); return -3; }
+  return 0;
+}
+
 }  // namespace gemm
 
 extern "C" {
@@ -362,6 +544,9 @@ int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias
                         int out_bf16, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0) { gemm::g_err = "bad shape (K must be a multiple of 8)"; return -4; }
   if (((uintptr_t)a | (uintptr_t)b) & 15) { gemm::g_err = "operands must be 16-byte aligned"; return -5; }
+  static const int mode = [] { const char* e = getenv("B200DIST_GEMM_PERSISTENT"); return e ? atoi(e) : 1; }();
+  if (mode && N >= 192 && (long long)((M + 127) / 128) * ((N + 255) / 256) >= 32)
+    return gemm::launch_persistent(a, b, c, bias, M, N, K, relu, out_bf16, stream);
   if (N <= 32) return gemm::launch<32>(a, b, c, bias, M, N, K, relu, out_bf16, stream);
   if (N <= 64) return gemm::launch<64>(a, b, c, bias, M, N, K, relu, out_bf16, stream);
   return gemm::launch<128>(a, b, c, bias, M, N, K, relu, out_bf16, stream);

@@ -30,6 +30,19 @@ struct SgdArgs {
 
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   const int rank = a.rank, world = a.world;
+  // Step parity (which gradient bucket is live) + step bump.  Thread 0 of every block reads the counter and then
+  // checks in with an atomic; the LAST block to check in knows every block has read it and bumps it right away, so
+  // the atomic's latency hides behind the rest of the kernel and no block can see the new value.
+  __shared__ unsigned int s_par;
+  if (threadIdx.x == 0) {
+    unsigned long long st = a.step != nullptr ? *reinterpret_cast<volatile unsigned long long*>(a.step) : 0ull;
+    s_par = (unsigned int)(st & 1ull);
+    if (a.step != nullptr) {
+      const unsigned int seen = atomicAdd(a.done_counter, 1u);
+      if (seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
+    }
+  }
+  __syncthreads();
   uint32_t epoch = 0;
   if (world > 1) {
     epoch = barrier_epoch_load(a.sig, rank);
@@ -39,7 +52,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   // Double-buffered buckets remove the second barrier: once every rank has arrived at THIS step's barrier it has
   // finished reading last step's bucket, so that one can be zeroed right away for the step after this one.
   const bool dbuf = a.grad_stride > 0;
-  const size_t par = (dbuf && a.step != nullptr) ? (size_t)(*a.step & 1ull) : 0;
+  const size_t par = dbuf ? (size_t)s_par : 0;
   const size_t cur_off = par * (size_t)a.grad_stride * sizeof(float);
   const size_t oth_off = (par ^ 1) * (size_t)a.grad_stride * sizeof(float);
   // block-uniform trip count (barrier inside the loop)
@@ -76,15 +89,6 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
     }
   }
   if (world > 1 && threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
-  // every block read `*a.step` at its start; the bump must not overtake a late block -> last block to finish bumps it
-  if (a.step != nullptr) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned int done = atomicAdd(a.done_counter, 1u);
-      if (done == gridDim.x - 1) { *a.done_counter = 0u; __threadfence(); *a.step += 1ull; }
-    }
-  }
 }
 
 // Plain flat momentum SGD (generic models: gradients already averaged in `grad`)

@@ -164,7 +164,7 @@ def test_fused_trainer_short_batch_and_device_input(dev):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 50, 320), (1000, 10, 512), (300, 200, 136), (64, 32, 8),
-                                   (4096, 512, 1024)])
+                                   (4096, 512, 1024), (4096, 256, 512), (2000, 1000, 264), (8192, 1003, 520)])
 def test_tcgen05_gemm_matches_torch(dev, M, N, K):
     from dist_tuto.pth_b200.ops.gemm import linear_bf16
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
@@ -229,38 +229,49 @@ def tc_mode():
 
 @pytest.mark.parametrize("B", [1, 16, 128, 200])
 def test_convnet_tcgen05_path_matches_fp64_oracle(dev, tc_mode, B):
-    """conv2 forward + data-gradient on the tensor cores (bf16 operands, fp32 accumulate in TMEM)."""
+    """conv2 forward + data-gradient on the tensor cores (bf16 operands, fp32 accumulate in TMEM).
+
+    bf16 rounding of the conv2 operands can flip a max-pool argmax / relu on near-ties, which reroutes a
+    gradient entry completely, so gradients are compared by direction (cosine) and a loose max-error bound,
+    while forward/loss are compared tightly."""
     from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, convnet_forward, pack_params, unpack_params
     net = _net(dev, seed=3).eval()
     x, y = _batch(dev, B, seed=5)
     flat = pack_params(net)
     out = convnet_forward(flat, x)
     ref_out = net(x)
-    assert torch.allclose(out, ref_out, atol=3e-2, rtol=3e-2), float((out - ref_out).abs().max())
+    assert torch.allclose(out, ref_out, atol=5e-3, rtol=5e-3), float((out - ref_out).abs().max())
     loss, grads = convnet_loss_and_grads(flat, x, y, training=False)
     net64 = net.double()
     ref_loss = F.nll_loss(net64(x.double()), y)
     ref_loss.backward()
-    assert abs(float(loss) - float(ref_loss)) < 2e-2 * max(1.0, abs(float(ref_loss)))
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss)))
     views = unpack_params(grads)
-    errs = {}
     for name, p in net64.named_parameters():
-        scale = p.grad.abs().max().clamp_min(1e-9)
-        errs[name] = float((views[name].double() - p.grad).abs().max() / scale)
-    assert max(errs.values()) < 5e-2, errs
-    # the two paths must agree with each other much more tightly than bf16 noise on everything downstream of conv2
-    assert errs["fc2.weight"] < 3e-2 and errs["conv1.weight"] < 5e-2
+        got, ref = views[name].double().flatten(), p.grad.flatten()
+        cos = float(torch.dot(got, ref) / (got.norm() * ref.norm()).clamp_min(1e-30))
+        rel = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        assert cos > 0.995 and rel < 0.2, (name, cos, rel)
 
 
-def test_convnet_tcgen05_training_with_dropout(dev, tc_mode):
+def test_convnet_tcgen05_training_tracks_simt(dev):
+    from dist_tuto.pth_b200.ops import _ext
     from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
-    tr = FusedTrainer(64, lr=0.05, seed=1, device=dev, p_drop=0.5)
-    g = torch.Generator().manual_seed(0)
-    losses = []
-    xs = torch.randn(64, 1, 28, 28, generator=g)
-    ys = torch.randint(0, 10, (64,), generator=g)
-    for i in range(30):                                   # overfit one batch: loss must fall
-        tr.step(xs.pin_memory(), ys.pin_memory())
-        if i in (0, 29):
-            losses.append(tr.pop_loss_sum())
-    assert losses[1] < losses[0], losses
+    C = _ext.C()
+    prev = C.convnet_get_tc()
+    curves = []
+    try:
+        for mode in (False, True):
+            C.convnet_set_tc(mode)
+            tr = FusedTrainer(64, lr=0.01, seed=1, device=dev, p_drop=0.5)
+            g = torch.Generator().manual_seed(0)
+            xs = torch.randn(64, 1, 28, 28, generator=g).pin_memory()
+            ys = torch.randint(0, 10, (64,), generator=g).pin_memory()
+            c = []
+            for _ in range(20):
+                tr.step(xs, ys)
+                c.append(tr.pop_loss_sum())
+            curves.append(c)
+    finally:
+        C.convnet_set_tc(prev)
+    assert all(abs(a - b) < 2e-2 for a, b in zip(*curves)), curves
