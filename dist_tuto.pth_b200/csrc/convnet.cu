@@ -29,6 +29,7 @@ constexpr int T = 512;              // 16 warps per sample: the phases are laten
 //   TC path   : bf16 UMMA operand tiles (K-major, 128B swizzle) for the two tcgen05 GEMMs of conv2
 //               forward  D[64 pos x 32 co]   = im2col(p1)[64 x 256] * W2[32 x 256]^T
 //               dgrad    D[64 pos x 256 k']  = dC[64 x 32 co]       * W2^T[256 x 32]^T      (k' = (ci/5)*128 + (ci%5)*25 + tap)
+//               wgrad    D[64 co  x 256 k ]  = dC^T[64 x 64 pos]    * im2col(p1)^T[256 x 64]^T
 struct SimtBufs {
   float w2f[250 * 20];      // [ci][ky][kx][co]          forward: 4 output channels per float4
   float w2b[500 * 16];      // [co][ky][kx][half][8]     backward-data: 5 input channels per (half)
@@ -40,6 +41,7 @@ struct TcBufs {
   unsigned char Bt[32768];      // W2^T as B operand (dgrad): [256 rows x 128 B] (K = co, 32 used)
   unsigned char A[4 * 8192];    // im2col(p1) as A operand: 4 K-blocks x [64 rows x 128 B]; later dA staging [64][128] fp32
   unsigned char Ad[8192];       // dC as A operand (dgrad) [64 rows x 128 B]; fwd: conv2 output staging [64][32] fp32
+  unsigned char Adt[8192];      // dC^T as A operand (wgrad) [64 rows (co) x 64 positions]
 };
 union Scratch {
   SimtBufs simt;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       for (int i = tid; i < (16384 + 32768) / 16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
       if (tid < 256) s.koff[tid] = tid < 250 ? (short)((tid / 25) * 144 + ((tid % 25) / 5) * 12 + (tid % 5)) : (short)-1;
       if (tid == 0) { tc::mbar_init(reinterpret_cast<uint64_t*>(&s.mma_bar), 1); tc::mbar_fence_init(); }
-      if ((tid >> 5) == 1) tc::tmem_alloc<256>(&s.tmem_slot);
+      if ((tid >> 5) == 1) tc::tmem_alloc<512>(&s.tmem_slot);
       __syncthreads();
     }
 #pragma unroll
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     __syncthreads();
 
     // -------------------------------------------------------------- S7a: conv2 weight/bias gradient (sparse)
-    for (int item = tid; item < 1000; item += T) {          // item = (co, ci, ky): 5 taps (kx) x 16 pooled cells
+    for (int item = tid; item < (TC ? 0 : 1000); item += T) {   // item = (co, ci, ky): 5 taps (kx) x 16 pooled cells  (TC: tcgen05 wgrad below)
       const int co = item / 50, r = item - co * 50, ci = r / 5, ky = r - ci * 5;
       float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -478,9 +480,9 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
       s.g[B2 + co] += d;
     }
-    // -------------------------------------------------------------- S7b/S8a: conv2 data gradient -> gradient at conv1's pooled argmax
+    // -------------------------------------------------------------- S7b/S8a: conv2 weight + data gradients on tcgen05
     if (TC) {
-      // dC[64 pos][co] (one non-zero per pool window and channel) as the bf16 A operand; K = co (32 of the 64 columns used)
+      // (1) dC[64 pos][co] (one non-zero per pool window and channel) as the bf16 A operand of the dgrad GEMM
       if (tid < 256) {
         const int r = tid >> 2, c8 = tid & 3, oy = r >> 3, ox = r & 7;
         const int cell = (oy >> 1) * 4 + (ox >> 1), sub = (oy & 1) * 2 + (ox & 1);
@@ -493,6 +495,31 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         const uint4 pk = make_uint4(b2::pack_bf16x2(f[0], f[1]), b2::pack_bf16x2(f[2], f[3]), b2::pack_bf16x2(f[4], f[5]),
                                     b2::pack_bf16x2(f[6], f[7]));
         *reinterpret_cast<uint4*>(s.u.tc.Ad + (r >> 3) * 1024 + (r & 7) * 128 + (((c8 ^ (r & 7)) & 7) << 4)) = pk;
+      } else if (tid < 256 + 160) {
+        // (2) dC^T[co][pos] as the A operand of the wgrad GEMM (rows >= 20 are never read back)
+        const int q = tid - 256, co = q >> 3, oy = q & 7;              // chunk = 8 positions of output row oy
+        float f[8];
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox) {
+          const int cell = (oy >> 1) * 4 + (ox >> 1), sub = (oy & 1) * 2 + (ox & 1);
+          f[ox] = s.a2[co * 16 + cell] == sub ? s.g2[co * 16 + cell] : 0.f;
+        }
+        const uint4 pk = make_uint4(b2::pack_bf16x2(f[0], f[1]), b2::pack_bf16x2(f[2], f[3]), b2::pack_bf16x2(f[4], f[5]),
+                                    b2::pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(s.u.tc.Adt + (co >> 3) * 1024 + (co & 7) * 128 + (((oy ^ (co & 7)) & 7) << 4)) = pk;
+      }
+      // (3) im2col(p1)^T[k][pos] as the B operand of the wgrad GEMM: 256 rows x 8 chunks of 8 consecutive ox
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int chunk = tid + m * T, k = chunk >> 3, oy = chunk & 7;
+        const int ko = s.koff[k];
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (ko >= 0) {
+          const float* src = &s.p1[ko + oy * 12];
+          pk = make_uint4(b2::pack_bf16x2(src[0], src[1]), b2::pack_bf16x2(src[2], src[3]), b2::pack_bf16x2(src[4], src[5]),
+                          b2::pack_bf16x2(src[6], src[7]));
+        }
+        *reinterpret_cast<uint4*>(s.u.tc.A + (k >> 3) * 1024 + (k & 7) * 128 + (((oy ^ (k & 7)) & 7) << 4)) = pk;
       }
       tc::fence_proxy_async();
       tc::fence_before();
@@ -500,9 +527,13 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       if (tid == 0) {
         tc::fence_after();
         constexpr uint32_t idesc = tc::idesc_bf16(64, 256);
-        const uint32_t a0 = tc::smem_u32(s.u.tc.Ad), b0 = tc::smem_u32(s.u.tc.Bt);
-        tc::umma_bf16(tmem, tc::smem_desc_sw128(a0), tc::smem_desc_sw128(b0), idesc, 0u);
-        tc::umma_bf16(tmem, tc::smem_desc_sw128(a0 + 32), tc::smem_desc_sw128(b0 + 32), idesc, 1u);
+        const uint32_t ad = tc::smem_u32(s.u.tc.Ad), bt = tc::smem_u32(s.u.tc.Bt);
+        const uint32_t at = tc::smem_u32(s.u.tc.Adt), bi = tc::smem_u32(s.u.tc.A);
+        tc::umma_bf16(tmem, tc::smem_desc_sw128(ad), tc::smem_desc_sw128(bt), idesc, 0u);               // dgrad: K = co
+        tc::umma_bf16(tmem, tc::smem_desc_sw128(ad + 32), tc::smem_desc_sw128(bt + 32), idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                                                                      // wgrad: K = pos
+          tc::umma_bf16(tmem + 256, tc::smem_desc_sw128(at + k * 32), tc::smem_desc_sw128(bi + k * 32), idesc, k != 0 ? 1u : 0u);
         tc::commit(reinterpret_cast<uint64_t*>(&s.mma_bar));
       }
       tc::mbar_wait(reinterpret_cast<uint64_t*>(&s.mma_bar), mma_phase);
@@ -524,6 +555,21 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
               for (int c4 = 0; c4 < 8; ++c4)
                 dst[(cc * 8 + c4) ^ (row & 31)] = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
                                                               __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+            }
+          }
+        } else if (tid < 192) {
+          // conv2.weight gradient: accumulator rows = co (rows 0..15 in lanes 0..15 of quadrant 0, rows 16..19 in quadrant 1)
+          const int q = (tid >> 5) & 3, lane = tid & 31, co = q * 16 + lane;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + half * 128 + cc * 32), r);
+            tc::tmem_ld_wait();
+            if (lane < 16 && co < 20) {
+              float* dst = &s.g[W2 + co * 250 + half * 128 + cc * 32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (half * 128 + cc * 32 + i < 250) dst[i] += __uint_as_float(r[i]);
             }
           }
         }
@@ -653,7 +699,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   if (TC) {
     tc::fence_before();
     __syncthreads();
-    if ((tid >> 5) == 1) { tc::fence_after(); tc::tmem_dealloc<256>(tmem); }
+    if ((tid >> 5) == 1) { tc::fence_after(); tc::tmem_dealloc<512>(tmem); }
   }
 }
 

@@ -120,9 +120,11 @@ class SymmWorld:
         # every CTA of a comm kernel spins on peer flags, so the grid never exceeds what is co-resident (1 CTA / SM)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.max_blocks = _env_int("B200DIST_AR_BLOCKS", 0) or min(sms, 148)
-        # size thresholds (wire bytes); overridable, see bench/allreduce_sweep.py for the measured table
-        self.oneshot_max = _env_int("B200DIST_ONESHOT_MAX", 512 << 10)
-        self.nvls_min = _env_int("B200DIST_NVLS_MIN", 256 << 10)
+        # size thresholds (wire bytes) from the measured sweeps (profiles/n2, profiles/n8; bench/allreduce_sweep.py):
+        #   2 GPUs : one-shot wins up to ~64 KB, two-shot above; NVLS never beats two-shot (no fan-in to amortise)
+        #   8 GPUs : one-shot wins up to ~8 KB; above that NVLS (in-switch reduction) wins at every size, two-shot next
+        self.oneshot_max = _env_int("B200DIST_ONESHOT_MAX", (64 << 10) if self.world <= 2 else (8 << 10))
+        self.nvls_min = _env_int("B200DIST_NVLS_MIN", (1 << 62) if self.world <= 2 else (8 << 10) + 1)
         self.nvls_error: Optional[str] = None
 
     # ------------------------------------------------------------------ plumbing
@@ -242,9 +244,9 @@ class SymmWorld:
         if forced in VARIANTS:
             v = VARIANTS[forced]
             return v if (v != 2 or self.multicast) else 1
-        if wire_bytes <= self.oneshot_max and not (self.multicast and wire_bytes >= self.nvls_min):
+        if wire_bytes <= self.oneshot_max:
             return 0
-        return 2 if self.multicast else 1
+        return 2 if (self.multicast and wire_bytes >= self.nvls_min) else 1
 
     def _launch(self, hd: SymmHandle, bf16: bool, n_vec: int, scale: float, src, dst, variant: Optional[int],
                 max_blocks: Optional[int] = None):
