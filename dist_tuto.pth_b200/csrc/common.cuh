@@ -19,6 +19,13 @@ struct PeerPtrs {                    // passed by value: per-rank base pointers 
 
 namespace b2 {
 
+// ----------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream/graph may start launching now (its CTAs then park in pdl_wait);
+// pdl_wait: blocks until the previous kernel has completed and its writes are visible.  Both are no-ops when the
+// kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------- memory model helpers
 __device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");

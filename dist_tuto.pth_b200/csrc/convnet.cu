@@ -15,6 +15,7 @@
 //   fc2.b 21836 | total 21848
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -103,14 +104,23 @@ struct Args {
 
 template <bool TC>
 __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // the kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's (1024-byte aligned)
+  // shared space: addresses stay compile-time constants (a run-time round-up costs an extra add on every access)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x;
+  if (TC && (tc::smem_u32(smem_raw) & 1023u) != 0u) __trap();   // UMMA SWIZZLE_128B tiles need 1024-byte alignment
   uint32_t mma_phase = 0;            // parity of the next "accumulator ready" wait (uniform across the CTA)
   uint32_t tmem = 0;
   const float* __restrict__ P = a.params;
 
   // ---------------------------------------------------------------- P0: stage weights, zero accumulators
+  b2::pdl_launch_dependents();       // the all-reduce/SGD kernel may pre-launch; it parks in its own pdl_wait
+  if (a.backward) {                  // everything that does not depend on the previous kernel happens before pdl_wait
+    float4* g4 = reinterpret_cast<float4*>(s.g);
+    for (int i = tid; i < NPAR / 4; i += T) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  b2::pdl_wait();                    // parameters / step counter written by the previous all-reduce+SGD kernel
   {
     // all global loads are issued before their first use (one L2 round trip instead of a dependent chain)
     const float4* __restrict__ P4w2 = reinterpret_cast<const float4*>(P + W2);   // 1250 float4, 16B aligned
@@ -123,10 +133,6 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     const float w1v = tid < 250 ? __ldg(P + W1 + tid) : 0.f;
     const float w4v = tid < 500 ? __ldg(P + W4 + tid) : 0.f;
     const float bv = tid < 10 ? __ldg(P + B1 + tid) : (tid < 20 ? __ldg(P + B4 + tid - 10) : (tid < 40 ? __ldg(P + B2 + tid - 20) : 0.f));
-    if (a.backward) {
-      float4* g4 = reinterpret_cast<float4*>(s.g);
-      for (int i = tid; i < NPAR / 4; i += T) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     if (tid < 250) s.w1[tid] = w1v;
     if (tid < 500) s.w4[tid] = w4v;
     if (tid < 10) s.b1[tid] = bv; else if (tid < 20) s.b4[tid - 10] = bv; else if (tid < 40) s.b2[tid - 20] = bv;
@@ -741,9 +747,21 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  if (b2_convnet_get_tc()) cn::convnet_step_kernel<true><<<grid, cn::T, smem, stream>>>(a);
-  else cn::convnet_step_kernel<false><<<grid, cn::T, smem, stream>>>(a);
-  return (int)cudaGetLastError();
+  static const int pdl = [] { const char* e = getenv("B200DIST_PDL"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)cn::T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = b2_convnet_get_tc() ? cudaLaunchKernelEx(&cfg, cn::convnet_step_kernel<true>, a)
+                                      : cudaLaunchKernelEx(&cfg, cn::convnet_step_kernel<false>, a);
+  return (int)e;
 }
 
 }  // extern "C"

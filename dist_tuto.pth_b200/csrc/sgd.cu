@@ -8,6 +8,8 @@
 // flag barrier that proves every peer has finished reading -- zeroes its own bucket for the next step's
 // `red.add` accumulation and bumps the device-side step counter used by the dropout RNG.
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 
 namespace b2 {
@@ -34,6 +36,8 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   // checks in with an atomic; the LAST block to check in knows every block has read it and bumps it right away, so
   // the atomic's latency hides behind the rest of the kernel and no block can see the new value.
   __shared__ unsigned int s_par;
+  pdl_wait();                        // gradients of this step (previous kernel) are complete and visible
+  pdl_launch_dependents();           // the next step's forward/backward kernel may pre-launch now (it zeroes its smem, then waits)
   if (threadIdx.x == 0) {
     unsigned long long st = a.step != nullptr ? *reinterpret_cast<volatile unsigned long long*>(a.step) : 0ull;
     s_par = (unsigned int)(st & 1ull);
@@ -133,8 +137,18 @@ int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, fl
   size_t blocks = (a.n_vec + b2::kSgdThreads - 1) / b2::kSgdThreads;
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;
-  b2::allreduce_sgd_kernel<<<(unsigned)blocks, b2::kSgdThreads, 0, stream>>>(a);
-  return (int)cudaGetLastError();
+  static const int pdl = [] { const char* e = getenv("B200DIST_PDL"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)b2::kSgdThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_kernel, a);
 }
 
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,

@@ -164,7 +164,8 @@ def test_fused_trainer_short_batch_and_device_input(dev):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 50, 320), (1000, 10, 512), (300, 200, 136), (64, 32, 8),
-                                   (4096, 512, 1024), (4096, 256, 512), (2000, 1000, 264), (8192, 1003, 520)])
+                                   (4096, 512, 1024), (4096, 256, 512), (2000, 1000, 264), (8192, 1003, 520),
+                                   (2500, 2048, 2056), (8192, 4096, 4096)])
 def test_tcgen05_gemm_matches_torch(dev, M, N, K):
     from dist_tuto.pth_b200.ops.gemm import linear_bf16
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
