@@ -70,6 +70,7 @@ struct __align__(1024) Smem {
   float g[NPAR];            // per-CTA gradient accumulators
   unsigned long long mma_bar;   // mbarrier: tcgen05.commit -> "accumulator ready"
   unsigned int tmem_slot;
+  int work_ctr;             // dynamic work distribution inside a phase (warp-granular)
   short koff[256];          // im2col LUT: k=(ci,ky,kx) -> offset inside p1, -1 for the K padding
   unsigned char a1[1440];   // conv1 pool argmax (0..3)
   unsigned char a2[320];    // conv2 pool argmax (0..3)
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         gw3[e4] = gv;
       }
       if (tid >= 320 && tid < 370) s.g[B3 + tid - 320] += s.dh[tid - 320];
+      if (tid == 511) s.work_ctr = 0;
       for (int o = tid; o < 320; o += T) {
         float d = 0.f;
 #pragma unroll 10
@@ -461,31 +463,44 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     __syncthreads();
 
     // -------------------------------------------------------------- S7a: conv2 weight/bias gradient (sparse)
-    for (int item = tid; item < (TC ? 0 : 1000); item += T) {   // item = (co, ci, ky): 5 taps (kx) x 16 pooled cells  (TC: tcgen05 wgrad below)
-      const int co = item / 50, r = item - co * 50, ci = r / 5, ky = r - ci * 5;
-      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    // Work items are handed out 32 at a time per warp from a shared counter, so the warps that had no (or a short)
+    // S7b tile start here immediately and the phase ends balanced.  item < 1000: (co, ci, ky) = 5 taps x 16 pooled
+    // cells; item 1000..1019: bias gradient of channel item-1000.  (TC mode: weight items are done by tcgen05.)
+    auto s7a = [&]() {
+      for (;;) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&s.work_ctr, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= 1020) break;
+        const int item = base + (tid & 31);
+        if (item < 1000) {
+          if (!TC) {
+            const int co = item / 50, r = item - co * 50, ci = r / 5, ky = r - ci * 5;
+            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-      for (int cell = 0; cell < 16; ++cell) {
-        const float gv = s.g2[co * 16 + cell];
-        if (gv != 0.f) {
-          const int arg = s.a2[co * 16 + cell];
-          const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
-          const float* src = &s.p1[ci * 144 + (ay + ky) * 12 + ax];
+            for (int cell = 0; cell < 16; ++cell) {
+              const float gv = s.g2[co * 16 + cell];
+              if (gv != 0.f) {
+                const int arg = s.a2[co * 16 + cell];
+                const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
+                const float* src = &s.p1[ci * 144 + (ay + ky) * 12 + ax];
 #pragma unroll
-          for (int kx = 0; kx < 5; ++kx) acc[kx] = fmaf(gv, src[kx], acc[kx]);
+                for (int kx = 0; kx < 5; ++kx) acc[kx] = fmaf(gv, src[kx], acc[kx]);
+              }
+            }
+            float* dst = &s.g[W2 + co * 250 + ci * 25 + ky * 5];
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) dst[kx] += acc[kx];
+          }
+        } else if (item < 1020) {
+          const int co = item - 1000;
+          float d = 0.f;
+#pragma unroll
+          for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
+          s.g[B2 + co] += d;
         }
       }
-      float* dst = &s.g[W2 + co * 250 + ci * 25 + ky * 5];
-#pragma unroll
-      for (int kx = 0; kx < 5; ++kx) dst[kx] += acc[kx];
-    }
-    if (tid >= 488 && tid < 508) {                          // idle lanes of the second pass: bias gradient
-      const int co = tid - 488;
-      float d = 0.f;
-#pragma unroll
-      for (int cell = 0; cell < 16; ++cell) d += s.g2[co * 16 + cell];
-      s.g[B2 + co] += d;
-    }
+    };
     // -------------------------------------------------------------- S7b/S8a: conv2 weight + data gradients on tcgen05
     if (TC) {
       // (1) dC[64 pos][co] (one non-zero per pool window and channel) as the bf16 A operand of the dgrad GEMM
@@ -542,6 +557,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
           tc::umma_bf16(tmem + 256, tc::smem_desc_sw128(at + k * 32), tc::smem_desc_sw128(bi + k * 32), idesc, k != 0 ? 1u : 0u);
         tc::commit(reinterpret_cast<uint64_t*>(&s.mma_bar));
       }
+      s7a();                                                  // bias gradient (20 items) while the MMAs run
       tc::mbar_wait(reinterpret_cast<uint64_t*>(&s.mma_bar), mma_phase);
       mma_phase ^= 1;
       tc::fence_after();
@@ -649,6 +665,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         dst[0] = acc[0][c]; dst[1] = acc[1][c]; dst[12] = acc[2][c]; dst[13] = acc[3][c];
       }
     }
+    s7a();
     __syncthreads();
 
     // -------------------------------------------------------------- S8a: through relu+pool of conv1

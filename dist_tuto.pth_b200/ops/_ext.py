@@ -38,13 +38,12 @@ def C():
         if _mod is not None:
             return _mod
         if not os.path.isfile(_SO):
-            if os.environ.get("B200DIST_AUTOBUILD", "0") == "1":
+            if os.environ.get("B200DIST_AUTOBUILD", "1") == "1":       # build the real thing (never a PyTorch fallback)
                 from .. import build as _b
                 _b.build(verbose=False)
             else:
                 raise ImportError(f"native extension missing: {_SO}\n"
-                                  "build it with:  python -c 'import __graft_entry__ as g; g.build()'  "
-                                  "(or set B200DIST_AUTOBUILD=1)")
+                                  "build it with:  python -c 'import __graft_entry__ as g; g.build()'")
         import torch  # noqa: F401  (libtorch must be loaded first)
         spec = importlib.util.spec_from_file_location("dist_tuto.pth_b200._C", _SO)
         mod = importlib.util.module_from_spec(spec)
