@@ -80,8 +80,13 @@ def main():
         dc = torch.zeros(1, dtype=torch.int32, device=dev)
         sg = timeit(lambda: C.allreduce_sgd([grads.data_ptr()], [0], params.clone(), mom, step, 0.01, 0.5, 1.0, 0, 1, True, 0, dc))
         flop = 2.9e6 * B
-        out["convnet"].append({"B": B, "fwd_bwd": fb, "fwd": fw, "sgd": sg, "samples_per_s_kernel": B / (fb["us_median"] * 1e-6),
-                               "gflops": flop / (fb["us_median"] * 1e-6) / 1e9})
+        row = {"B": B, "fwd_bwd": fb, "fwd": fw, "sgd": sg, "samples_per_s_kernel": B / (fb["us_median"] * 1e-6),
+               "gflops": flop / (fb["us_median"] * 1e-6) / 1e9}
+        for cl in (2, 4, 8):                    # one cluster of `cl` CTAs per sample (one wave only)
+            if B * cl <= 128:
+                row[f"fwd_bwd_cluster{cl}"] = timeit(lambda: C.convnet_step(params, grads, x, y, acc, None, None, step, 1, 0, True,
+                                                                            1.0 / B, 0.5, 0, 0, cl))
+        out["convnet"].append(row)
     print(json.dumps(out, indent=1))
 
 

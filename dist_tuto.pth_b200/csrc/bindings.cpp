@@ -51,6 +51,11 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream);
+int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
+                              float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
+                              unsigned long long seed, long long sample_base, int B, int training, int backward,
+                              float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
+                              cudaStream_t stream);
 void b2_convnet_set_tc(int on);
 int b2_convnet_get_tc();
 int b2_gemm_available();
@@ -138,7 +143,7 @@ struct ExecutorPy {
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
-             int max_in_flight)
+             int max_in_flight, int cluster)
       : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
@@ -156,7 +161,7 @@ struct ExecutorPy {
     c.in_dev[0] = in_dev.data_ptr<uint8_t>(); c.in_dev[1] = in_dev.data_ptr<uint8_t>() + block;
     c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
     c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;
-    c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop;
+    c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop; c.cluster = cluster;
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
     impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
@@ -257,7 +262,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("convnet_step", [](torch::Tensor params, c10::optional<torch::Tensor> grads, torch::Tensor x, torch::Tensor target,
                            c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
                            c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
-                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride) {
+                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride, int cluster) {
     check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
     TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
@@ -274,12 +279,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (mask_out.has_value()) { TORCH_CHECK(mask_out->numel() == (int64_t)B * 70 && mask_out->scalar_type() == torch::kFloat32); mo = mask_out->data_ptr<float>(); }
     const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
     c10::cuda::CUDAGuard guard(params.device());
+    if (cluster > 1) {
+      TORCH_CHECK(cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 1, 2, 4 or 8");
+      ck_cuda(b2_convnet_cluster_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
+                                        la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
+                                        cluster, max_ctas, grad_stride, cur_stream()), "convnet_cluster launch");
+      return;
+    }
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
                                    max_ctas, grad_stride, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
-     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0);
+     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1);
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });
@@ -312,12 +324,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<ExecutorPy>(m, "StepExecutor")
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
-                    int, int, uint64_t, int64_t, int64_t, double, double, double, int>(),
+                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
-           py::arg("max_in_flight") = 3, py::keep_alive<1, 2>())
+           py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::keep_alive<1, 2>())
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
       .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
       .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });

@@ -18,11 +18,10 @@
 #include <cstring>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "convnet_args.cuh"
 
 namespace cn {
 
-constexpr int W1 = 0, B1 = 252, W2 = 264, B2 = 5264, W3 = 5284, B3 = 21284, W4 = 21336, B4 = 21836;
-constexpr int NPAR = 21848;
 constexpr int T = 512;              // 16 warps per sample: the phases are latency-bound, so more warps per CTA
 
 // The conv2 working set exists in two flavours that share one union:
@@ -76,31 +75,6 @@ struct __align__(1024) Smem {
   unsigned char a2[320];    // conv2 pool argmax (0..3)
   float loss_local;
   int correct_local;
-};
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-struct Args {
-  const float* params;      // flat fp32 [NPAR]
-  float* grads;             // flat fp32 [NPAR], accumulated with red.add (caller keeps it zeroed)
-  const void* x;            // [B,1,28,28] fp32 (normalised) or uint8 (raw, normalised here)
-  const long long* target;  // [B]
-  float* loss_acc;          // [0] += sum_b nll_b * inv_bsz ; [1] += #correct   (may be null)
-  float* out_logp;          // [B,10] log-probabilities (may be null)
-  float* mask_out;          // [B,70] dropout scales actually applied (debug/tests; may be null)
-  const unsigned long long* step;   // device step counter (RNG offset); may be null -> 0
-  unsigned long long seed;
-  long long sample_base;    // global index of sample 0 (rank * bsz): decorrelates ranks
-  int B;
-  int x_u8;
-  int training;             // dropout on/off
-  int backward;             // compute gradients
-  float inv_bsz;            // 1 / local batch (nll_loss mean)
-  float p_drop;
-  float mean, inv_std;      // uint8 normalisation
-  long long grad_stride;    // elements between the two gradient buckets (0: single bucket); bucket = step & 1
 };
 
 template <bool TC>

@@ -24,6 +24,11 @@ struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream);
+int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
+                              float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
+                              unsigned long long seed, long long sample_base, int B, int training, int backward,
+                              float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
+                              cudaStream_t stream);
 int b2_convnet_npar();
 }
 
@@ -69,9 +74,13 @@ bool StepExecutor::capture(int parity) {
   if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
   const void* x = cfg_.in_dev[parity];
   const long long* y = reinterpret_cast<const long long*>(cfg_.in_dev[parity] + loader_->y_offset());
-  int rc = b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
-                                  cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
-                                  cfg_.p_drop, 0, cfg_.grad_stride, compute_);
+  int rc = cfg_.cluster > 1
+               ? b2_convnet_cluster_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
+                                           cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1,
+                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, compute_)
+               : b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
+                                        cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
+                                        cfg_.p_drop, 0, cfg_.grad_stride, compute_);
   PeerPtrsC g;
   SignalPadsC sg;
   std::memcpy(g.p, cfg_.grad_ptrs, sizeof(g.p));

@@ -21,7 +21,7 @@ struct StepConfig {
   unsigned int* done_counter;
   float* loss_acc;                   // [2]
   unsigned char* in_dev[2];          // double-buffered device input blocks, same layout as a loader slot: [x | pad | y]
-  int B, x_u8, training, rank, world;
+  int B, x_u8, training, rank, world, cluster;
   unsigned long long seed;
   long long sample_base, grad_stride;
   float lr, mu, p_drop;

@@ -61,9 +61,25 @@ def pack_params(src, device=None) -> torch.Tensor:
     return flat
 
 
+def pick_cluster(bsz: int) -> int:
+    """CTAs per sample for the fused step: the largest of 8/4/2 that still fits one wave (bsz * C <= 128), else 1.
+
+    With the reference's fixed global batch of 128 a GPU holds 128/N samples; a cluster per sample turns the idle SMs
+    into a shorter per-sample latency (csrc/convnet_cluster.cu).  ``B200DIST_CONVNET_CLUSTER`` overrides."""
+    import os
+    env = os.environ.get("B200DIST_CONVNET_CLUSTER")
+    if env is not None:
+        return int(env)
+    for c in (8, 4, 2):
+        if bsz * c <= 128:
+            return c
+    return 1
+
+
 def convnet_loss_and_grads(params: torch.Tensor, x: torch.Tensor, target: torch.Tensor, training: bool = False,
                            seed: int = 0, step: Optional[torch.Tensor] = None, sample_base: int = 0,
-                           p_drop: float = 0.5, return_masks: bool = False, grads: Optional[torch.Tensor] = None):
+                           p_drop: float = 0.5, return_masks: bool = False, grads: Optional[torch.Tensor] = None,
+                           cluster: int = 1):
     """Functional entry: returns ``(mean_nll, grads_flat[, masks])`` for one batch (used by tests)."""
     C = _ext.C()
     B = target.numel()
@@ -72,7 +88,7 @@ def convnet_loss_and_grads(params: torch.Tensor, x: torch.Tensor, target: torch.
     acc = torch.zeros(2, dtype=torch.float32, device=params.device)
     masks = torch.empty(B, 70, dtype=torch.float32, device=params.device) if return_masks else None
     C.convnet_step(params, grads, x.contiguous(), target.contiguous(), acc, None, masks, step, seed, sample_base,
-                   training, 1.0 / B, p_drop, 0)
+                   training, 1.0 / B, p_drop, 0, 0, cluster)
     return (acc[0], grads, masks) if return_masks else (acc[0], grads)
 
 
@@ -95,7 +111,7 @@ class FusedTrainer:
 
     def __init__(self, bsz: int, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234, device=None,
                  p_drop: float = 0.5, group=None, raw_uint8: bool = False, num_slots: int = 4,
-                 use_graph: bool = True, init_from: Optional[Net] = None):
+                 use_graph: bool = True, init_from: Optional[Net] = None, cluster: Optional[int] = None):
         self.C = _ext.C()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.bsz, self.lr, self.mu, self.seed, self.p_drop = int(bsz), float(lr), float(momentum), int(seed), p_drop
@@ -104,6 +120,7 @@ class FusedTrainer:
         self.rank = comm.group_ranks(group).index(comm.get_rank()) if comm.is_initialized() else 0
         self.raw_uint8 = raw_uint8
         self.training = True
+        self.cluster = pick_cluster(self.bsz) if cluster is None else int(cluster)
         # identical replicas: same seed AND an explicit broadcast (the reference relies on the seed only)
         if init_from is None:
             torch.manual_seed(seed)
@@ -155,7 +172,8 @@ class FusedTrainer:
     # ------------------------------------------------------------------ kernels
     def _kernels(self, x, y, B):
         self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
-                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride)
+                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride,
+                            self.cluster if B * self.cluster <= 148 else 1)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
                              self.done_counter)
@@ -272,7 +290,8 @@ class FusedTrainer:
             ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
-                                      self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2)),
+                                      self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
+                                      self.cluster),
                   self.training)
             self._executors[id(loader)] = ex
         if new_epoch:

@@ -276,3 +276,51 @@ def test_convnet_tcgen05_training_tracks_simt(dev):
     finally:
         C.convnet_set_tc(prev)
     assert all(abs(a - b) < 2e-2 for a, b in zip(*curves)), curves
+
+
+@pytest.mark.parametrize("cluster,B", [(2, 1), (2, 64), (4, 5), (4, 32), (8, 1), (8, 16), (8, 40)])
+def test_convnet_cluster_per_sample_matches_fp64_oracle(dev, cluster, B):
+    """One thread-block cluster (2/4/8 CTAs, DSMEM broadcasts) per sample: same numerics as the one-CTA kernel."""
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, pack_params, unpack_params
+    net = _net(dev, seed=3).eval()
+    x, y = _batch(dev, B, seed=5)
+    flat = pack_params(net)
+    loss, grads = convnet_loss_and_grads(flat, x, y, training=False, cluster=cluster)
+    net64 = net.double()
+    ref_loss = F.nll_loss(net64(x.double()), y)
+    ref_loss.backward()
+    assert torch.allclose(loss.double(), ref_loss, atol=1e-4, rtol=1e-4)
+    views = unpack_params(grads)
+    errs = {}
+    for name, p in net64.named_parameters():
+        scale = p.grad.abs().max().clamp_min(1e-9)
+        errs[name] = float((views[name].double() - p.grad).abs().max() / scale)
+    assert max(errs.values()) < 1e-3, errs
+    assert float(grads[250:252].abs().sum()) == 0.0
+
+
+def test_convnet_cluster_dropout_masks_match_single_cta_kernel(dev):
+    from dist_tuto.pth_b200.ops.convnet_fused import convnet_loss_and_grads, pack_params
+    net = _net(dev, seed=4).eval()
+    x, y = _batch(dev, 16, seed=6)
+    flat = pack_params(net)
+    step = torch.tensor([5], dtype=torch.int64, device=dev)
+    l1, g1, m1 = convnet_loss_and_grads(flat, x, y, training=True, seed=9, step=step, return_masks=True, cluster=1)
+    l8, g8, m8 = convnet_loss_and_grads(flat, x, y, training=True, seed=9, step=step, return_masks=True, cluster=8)
+    assert torch.equal(m1, m8)
+    assert torch.allclose(l1, l8, atol=1e-5)
+    assert torch.allclose(g1, g8, atol=1e-5, rtol=1e-4)
+
+
+def test_fused_trainer_uses_clusters_for_small_batches(dev):
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer, pick_cluster
+    assert [pick_cluster(b) for b in (128, 64, 32, 16, 8)] == [1, 2, 4, 8, 8]
+    res = []
+    for cluster in (1, 8):
+        tr = FusedTrainer(16, lr=0.05, seed=3, device=dev, p_drop=0.5, cluster=cluster)
+        g = torch.Generator().manual_seed(1)
+        for i in range(8):
+            tr.step(torch.randn(16, 1, 28, 28, generator=g).pin_memory(), torch.randint(0, 10, (16,), generator=g).pin_memory())
+        res.append((tr.pop_loss_sum(), tr.params.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-3
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-5, rtol=1e-4)
