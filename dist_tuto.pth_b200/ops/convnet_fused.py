@@ -62,17 +62,22 @@ def pack_params(src, device=None) -> torch.Tensor:
 
 
 def pick_cluster(bsz: int) -> int:
-    """CTAs per sample for the fused step: the largest of 8/4/2 that still fits one wave (bsz * C <= 128), else 1.
+    """CTAs per sample for the fused step (measured on B200, profiles/kernel_bench_v4.json).
 
-    With the reference's fixed global batch of 128 a GPU holds 128/N samples; a cluster per sample turns the idle SMs
-    into a shorter per-sample latency (csrc/convnet_cluster.cu).  ``B200DIST_CONVNET_CLUSTER`` overrides."""
+    With the reference's fixed global batch of 128 a GPU holds 128/N samples; a cluster per sample turns idle SMs into
+    a shorter per-sample latency (csrc/convnet_cluster.cu): 32.8 us (1 CTA) -> 28.7 (2) -> 24.6 (4).  Clusters of 8
+    only fit two per GPC with this kernel's 216 KB of shared memory per CTA, so 16 of them do not fit in one wave (46 us);
+    they are used only when the batch is <= 8.  ``B200DIST_CONVNET_CLUSTER`` overrides."""
     import os
     env = os.environ.get("B200DIST_CONVNET_CLUSTER")
     if env is not None:
         return int(env)
-    for c in (8, 4, 2):
-        if bsz * c <= 128:
-            return c
+    if bsz <= 8:
+        return 8
+    if bsz <= 32:
+        return 4
+    if bsz <= 64:
+        return 2
     return 1
 
 
