@@ -42,7 +42,7 @@ int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const Signa
 int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t stream);
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream);
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -50,12 +50,12 @@ int b2_convnet_npar();
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream);
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              cudaStream_t stream);
+                              const float* aux, cudaStream_t stream);
 void b2_convnet_set_tc(int on);
 int b2_convnet_get_tc();
 int b2_gemm_available();
@@ -143,8 +143,8 @@ struct ExecutorPy {
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
-             int max_in_flight, int cluster)
-      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev} {
+             int max_in_flight, int cluster, torch::Tensor aux)
+      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
     const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
@@ -162,6 +162,8 @@ struct ExecutorPy {
     c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
     c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;
     c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop; c.cluster = cluster;
+    TORCH_CHECK(aux.is_cuda() && aux.scalar_type() == torch::kFloat32 && aux.numel() >= 13000, "aux: CUDA fp32 [13000]");
+    c.aux = aux.data_ptr<float>();
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
     impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
@@ -230,7 +232,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("allreduce_sgd", [](std::vector<unsigned long long> grads, std::vector<unsigned long long> sigs, torch::Tensor params,
                             torch::Tensor momentum, c10::optional<torch::Tensor> step, double lr, double mu, double scale,
-                            int rank, int world, bool zero_grads, int64_t grad_stride, c10::optional<torch::Tensor> done_counter) {
+                            int rank, int world, bool zero_grads, int64_t grad_stride, c10::optional<torch::Tensor> done_counter,
+                            c10::optional<torch::Tensor> aux) {
     check_cuda_contig(params, "params"); check_cuda_contig(momentum, "momentum");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && momentum.scalar_type() == torch::kFloat32, "fp32 flat buffers");
     TORCH_CHECK(params.numel() % 4 == 0 && params.numel() == momentum.numel(), "flat buffers must be padded to 4 elements");
@@ -238,13 +241,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     unsigned long long* st = step.has_value() ? reinterpret_cast<unsigned long long*>(step->data_ptr()) : nullptr;
     unsigned int* dc = done_counter.has_value() ? reinterpret_cast<unsigned int*>(done_counter->data_ptr()) : nullptr;
     TORCH_CHECK(st == nullptr || dc != nullptr, "a step counter needs a done_counter scratch word");
+    float* ax = nullptr;
+    if (aux.has_value()) { TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == torch::kFloat32 && aux->numel() >= 13000); ax = aux->data_ptr<float>(); }
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
-                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, cur_stream()),
+                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax, cur_stream()),
             "allreduce_sgd launch");
   }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
      py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
-     py::arg("done_counter") = py::none());
+     py::arg("done_counter") = py::none(), py::arg("aux") = py::none());
   m.def("sgd_flat", [](torch::Tensor p, torch::Tensor mom, torch::Tensor g, double lr, double mu, double wd, bool zero_grad) {
     check_cuda_contig(p, "p"); check_cuda_contig(mom, "m"); check_cuda_contig(g, "g");
     TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
@@ -262,7 +267,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("convnet_step", [](torch::Tensor params, c10::optional<torch::Tensor> grads, torch::Tensor x, torch::Tensor target,
                            c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
                            c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
-                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride, int cluster) {
+                           int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride, int cluster,
+                           c10::optional<torch::Tensor> aux) {
     check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
     TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
@@ -279,19 +285,21 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (mask_out.has_value()) { TORCH_CHECK(mask_out->numel() == (int64_t)B * 70 && mask_out->scalar_type() == torch::kFloat32); mo = mask_out->data_ptr<float>(); }
     const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
     c10::cuda::CUDAGuard guard(params.device());
+    const float* ax = nullptr;
+    if (aux.has_value()) { TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == torch::kFloat32 && aux->numel() >= 13000); ax = aux->data_ptr<float>(); }
     if (cluster > 1) {
       TORCH_CHECK(cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 1, 2, 4 or 8");
       ck_cuda(b2_convnet_cluster_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                         la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                        cluster, max_ctas, grad_stride, cur_stream()), "convnet_cluster launch");
+                                        cluster, max_ctas, grad_stride, ax, cur_stream()), "convnet_cluster launch");
       return;
     }
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                   max_ctas, grad_stride, cur_stream()), "convnet_step launch");
+                                   max_ctas, grad_stride, ax, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
-     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1);
+     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none());
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });
@@ -324,12 +332,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<ExecutorPy>(m, "StepExecutor")
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
-                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int>(),
+                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
-           py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::keep_alive<1, 2>())
+           py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::keep_alive<1, 2>())
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
       .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
       .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });

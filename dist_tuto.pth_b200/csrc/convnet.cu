@@ -98,12 +98,21 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   b2::pdl_wait();                    // parameters / step counter written by the previous all-reduce+SGD kernel
   {
     // all global loads are issued before their first use (one L2 round trip instead of a dependent chain)
+    const bool fast = (a.aux != nullptr) && !TC;   // conv2.weight already in both smem layouts (written by sgd.cu)
+    if (fast) {
+      const float4* __restrict__ af = reinterpret_cast<const float4*>(a.aux + AUX_W2F);
+      const float4* __restrict__ ab = reinterpret_cast<const float4*>(a.aux + AUX_W2B);
+      float4* df = reinterpret_cast<float4*>(s.u.simt.w2f);
+      float4* db = reinterpret_cast<float4*>(s.u.simt.w2b);
+      for (int i = tid; i < 1250; i += T) df[i] = __ldg(af + i);
+      for (int i = tid; i < 2000; i += T) db[i] = __ldg(ab + i);
+    }
     const float4* __restrict__ P4w2 = reinterpret_cast<const float4*>(P + W2);   // 1250 float4, 16B aligned
     float4 v[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i4 = tid + k * T;
-      v[k] = i4 < 1250 ? __ldg(P4w2 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[k] = (!fast && i4 < 1250) ? __ldg(P4w2 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float w1v = tid < 250 ? __ldg(P + W1 + tid) : 0.f;
     const float w4v = tid < 500 ? __ldg(P + W4 + tid) : 0.f;
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i4 = tid + k * T;
-      if (i4 < 1250) {
+      if (!fast && i4 < 1250) {
         const float w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {             // conv2.weight [co][ci][ky][kx]
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         }
       }
     }
-  }
+    }
   if (tid == 0) { s.loss_local = 0.f; s.correct_local = 0; }
   const unsigned long long step = a.step ? *a.step : 0ull;
   const float keep_scale = 1.f / (1.f - a.p_drop);
@@ -720,7 +729,7 @@ int b2_convnet_get_tc() {
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream) {
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cn::Smem) + 1024;
   if (!configured) {
@@ -734,7 +743,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   a.params = params; a.grads = grads; a.x = x; a.target = target; a.loss_acc = loss_acc; a.out_logp = out_logp;
   a.mask_out = mask_out; a.step = step; a.seed = seed; a.sample_base = sample_base; a.B = B; a.x_u8 = x_u8;
   a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
-  a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride;
+  a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;

@@ -30,6 +30,9 @@ struct Args {
   float p_drop;
   float mean, inv_std;      // uint8 normalisation
   long long grad_stride;    // elements between the two gradient buckets (0: single bucket); bucket = step & 1
+  const float* aux;         // optional: conv2.weight pre-arranged by the SGD kernel as [w2f 5000 | w2b 8000] (see sgd.cu)
 };
+
+constexpr int AUX_W2F = 0, AUX_W2B = 5000, AUX_TOTAL = 13000;
 
 }  // namespace cn

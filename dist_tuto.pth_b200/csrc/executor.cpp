@@ -18,17 +18,17 @@ extern "C" {
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, cudaStream_t stream);
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream);
 struct PeerPtrsC { void* p[8]; };
 struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream);
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              cudaStream_t stream);
+                              const float* aux, cudaStream_t stream);
 int b2_convnet_npar();
 }
 
@@ -77,17 +77,17 @@ bool StepExecutor::capture(int parity) {
   int rc = cfg_.cluster > 1
                ? b2_convnet_cluster_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                            cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1,
-                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, compute_)
+                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, compute_)
                : b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                         cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
-                                        cfg_.p_drop, 0, cfg_.grad_stride, compute_);
+                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, compute_);
   PeerPtrsC g;
   SignalPadsC sg;
   std::memcpy(g.p, cfg_.grad_ptrs, sizeof(g.p));
   std::memcpy(sg.pad, cfg_.sig_ptrs, sizeof(sg.pad));
   int rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
                                     cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
-                                    cfg_.done_counter, compute_);
+                                    cfg_.done_counter, cfg_.aux, compute_);
   e = cudaStreamEndCapture(compute_, &graph);
   if (rc != 0 || rc2 != 0 || e != cudaSuccess || graph == nullptr) {
     err_ = std::string("graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : (cudaError_t)(rc ? rc : rc2));

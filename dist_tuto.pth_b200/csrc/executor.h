@@ -25,6 +25,7 @@ struct StepConfig {
   unsigned long long seed;
   long long sample_base, grad_stride;
   float lr, mu, p_drop;
+  float* aux;                        // conv2.weight in the kernels' smem layouts (maintained by the SGD kernel)
 };
 
 class StepExecutor {

@@ -28,6 +28,7 @@ struct SgdArgs {
   int rank, world;
   int zero_grads;
   long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
+  float* aux;                // optional [w2f 5000 | w2b 8000]: conv2.weight re-arranged for the forward/backward kernels
 };
 
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
@@ -82,6 +83,16 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
       p.x = fmaf(-a.lr, m.x, p.x); p.y = fmaf(-a.lr, m.y, p.y); p.z = fmaf(-a.lr, m.z, p.z); p.w = fmaf(-a.lr, m.w, p.w);
       reinterpret_cast<float4*>(a.momentum)[v] = m;
       reinterpret_cast<float4*>(a.params)[v] = p;
+      if (a.aux != nullptr && v >= 264 / 4 && v < (264 + 5000) / 4) {      // conv2.weight (flat offset 264, 5000 elements)
+        const float pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = (int)v * 4 + e - 264;
+          const int co = i / 250, r = i - co * 250, ci = r / 25, kk = r - ci * 25;
+          a.aux[(ci * 25 + kk) * 20 + co] = pw[e];                                     // w2f [ci][ky][kx][co]
+          a.aux[5000 + ((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = pw[e];            // w2b [co][ky][kx][half][8]
+        }
+      }
     }
     if (a.zero_grads) {
       if (dbuf) {
@@ -128,11 +139,11 @@ extern "C" {
 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, cudaStream_t stream) {
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream) {
   b2::SgdArgs a;
   a.grads = *grads; a.sig = *sig; a.params = params; a.momentum = momentum; a.step = step;
   a.n_vec = n_elems / 4; a.lr = lr; a.mu = mu; a.scale = scale; a.rank = rank; a.world = world;
-  a.zero_grads = zero_grads; a.grad_stride = grad_stride; a.done_counter = done_counter;
+  a.zero_grads = zero_grads; a.grad_stride = grad_stride; a.done_counter = done_counter; a.aux = aux;
   if (step != nullptr && done_counter == nullptr) return (int)cudaErrorInvalidValue;
   size_t blocks = (a.n_vec + b2::kSgdThreads - 1) / b2::kSgdThreads;
   if (blocks < 1) blocks = 1;

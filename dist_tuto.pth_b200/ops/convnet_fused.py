@@ -134,6 +134,9 @@ class FusedTrainer:
         if self.world > 1:
             dist.broadcast(self.params, src=comm.group_ranks(group)[0], group=comm._g(group))
         self.momentum = torch.zeros_like(self.params)
+        # conv2.weight pre-arranged in the two shared-memory layouts of the kernels; kept current by the SGD kernel
+        self.aux = torch.zeros(13000, dtype=torch.float32, device=self.device)
+        self._refresh_aux()
         self.symm = None
         self.grad_handle = None
         if self.world > 1:
@@ -174,14 +177,22 @@ class FusedTrainer:
         self.gpu_launches_per_step = 2              # convnet_step + allreduce_sgd (our kernels)
         self._warm()
 
+    def _refresh_aux(self):
+        """(Re)build the pre-arranged conv2.weight copies from the flat parameters (init / load_state_dict)."""
+        w2 = self.params[LAYOUT["conv2.weight"]:LAYOUT["conv2.weight"] + 5000].view(20, 10, 25)
+        self.aux[:5000].copy_(w2.permute(1, 2, 0).reshape(-1))                       # w2f [ci][k][co]
+        wb = torch.zeros(20, 25, 2, 8, dtype=torch.float32, device=self.device)
+        wb[:, :, :, :5] = w2.view(20, 2, 5, 25).permute(0, 3, 1, 2)                  # w2b [co][k][half][8]
+        self.aux[5000:].copy_(wb.reshape(-1))
+
     # ------------------------------------------------------------------ kernels
     def _kernels(self, x, y, B):
         self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
                             self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride,
-                            self.cluster if B * self.cluster <= 148 else 1)
+                            self.cluster if B * self.cluster <= 148 else 1, self.aux)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
-                             self.done_counter)
+                             self.done_counter, self.aux)
 
     def _warm(self):
         # forward-only launch: sets the kernel's dynamic-smem attribute outside of graph capture
@@ -296,7 +307,7 @@ class FusedTrainer:
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
-                                      self.cluster),
+                                      self.cluster, self.aux),
                   self.training)
             self._executors[id(loader)] = ex
         if new_epoch:
@@ -369,6 +380,7 @@ class FusedTrainer:
                 mv[k].copy_(v)
         if "steps" in sd:
             self.step_counter.fill_(int(sd["steps"]))
+        self._refresh_aux()
         torch.cuda.synchronize(self.device)
 
     def to_module(self) -> Net:
