@@ -124,8 +124,10 @@ def ours(args):
         if rank == 0:
             sym = tr.symm.describe() if tr.symm is not None else {"world": 1}
             print(result_line(impl="ours", value=value, ms=ms, n_gpus=size, steps=K, warmup=W, clocks=clk.summary(),
-                              e2e_value=e2e, h2d=h2d, d2h=8, gpu_launches=2 * K, dtype="fp32 (SIMT fused path; >= bf16)",
-                              extra_config={"engine": "fused convnet_step + allreduce_sgd kernels, CUDA graph",
+                              e2e_value=e2e, h2d=h2d, d2h=8, gpu_launches=2 * K, dtype="fp32",
+                              extra_config={"engine": "fused convnet_step (cluster-per-sample for small per-GPU batches) + allreduce_sgd kernels, CUDA graph, PDL",
+                                            "precision": "fp32 SIMT forward/backward (>= the required bf16); fp32 gradients on the wire; fp32 SGD",
+                                            "cluster_ctas_per_sample": tr.cluster,
                                             "l2": f"inputs cycle through a {pool * batch_bytes >> 20} MB device pool (> 126 MB L2)",
                                             "graph_chunk": G, "symm": sym,
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor (one cudaGraphLaunch "

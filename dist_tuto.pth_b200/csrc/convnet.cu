@@ -99,13 +99,14 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
   {
     // all global loads are issued before their first use (one L2 round trip instead of a dependent chain)
     const bool fast = (a.aux != nullptr) && !TC;   // conv2.weight already in both smem layouts (written by sgd.cu)
+    float4 fa[3], fb[4];            // pre-arranged conv2.weight: every load is in flight before the first store
     if (fast) {
       const float4* __restrict__ af = reinterpret_cast<const float4*>(a.aux + AUX_W2F);
       const float4* __restrict__ ab = reinterpret_cast<const float4*>(a.aux + AUX_W2B);
-      float4* df = reinterpret_cast<float4*>(s.u.simt.w2f);
-      float4* db = reinterpret_cast<float4*>(s.u.simt.w2b);
-      for (int i = tid; i < 1250; i += T) df[i] = __ldg(af + i);
-      for (int i = tid; i < 2000; i += T) db[i] = __ldg(ab + i);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fa[k] = (tid + k * T < 1250) ? __ldg(af + tid + k * T) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fb[k] = (tid + k * T < 2000) ? __ldg(ab + tid + k * T) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4* __restrict__ P4w2 = reinterpret_cast<const float4*>(P + W2);   // 1250 float4, 16B aligned
     float4 v[3];
@@ -128,6 +129,14 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       if (tid == 0) { tc::mbar_init(reinterpret_cast<uint64_t*>(&s.mma_bar), 1); tc::mbar_fence_init(); }
       if ((tid >> 5) == 1) tc::tmem_alloc<512>(&s.tmem_slot);
       __syncthreads();
+    }
+    if (fast) {
+      float4* df = reinterpret_cast<float4*>(s.u.simt.w2f);
+      float4* db = reinterpret_cast<float4*>(s.u.simt.w2b);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) if (tid + k * T < 1250) df[tid + k * T] = fa[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (tid + k * T < 2000) db[tid + k * T] = fb[k];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

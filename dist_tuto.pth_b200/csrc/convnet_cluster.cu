@@ -6,7 +6,7 @@
 // (C = 2, 4, 8 on as many SMs): every phase of the forward/backward pass is split C ways, the small activations every CTA
 // needs next (pooled conv outputs, fc1 activations, their gradients) are broadcast into all peers' shared memory with
 // distributed-shared-memory stores, and a cluster barrier (barrier.cluster arrive.release / wait.acquire) separates the
-// phases.  Weights are staged by every CTA (parallel L2 reads); each CTA flushes only the gradient slices it owns, so the
+// phases (4 per sample; fc1/fc2 and their small backward pieces are recomputed by every CTA instead of exchanged).  Weights are staged by every CTA (parallel L2 reads); each CTA flushes only the gradient slices it owns, so the
 // number of global `red.add` operations per sample stays 21,848 but is issued from C SMs at once.
 #include <cooperative_groups.h>
 
@@ -91,13 +91,14 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
   b2::pdl_wait();
   {
     const bool fast = (a.aux != nullptr);   // conv2.weight already in both smem layouts (written by sgd.cu)
+    float4 fa[3], fb[4];            // pre-arranged conv2.weight: every load is in flight before the first store
     if (fast) {
       const float4* __restrict__ af = reinterpret_cast<const float4*>(a.aux + AUX_W2F);
       const float4* __restrict__ ab = reinterpret_cast<const float4*>(a.aux + AUX_W2B);
-      float4* df = reinterpret_cast<float4*>(s.w2f);
-      float4* db = reinterpret_cast<float4*>(s.w2b);
-      for (int i = tid; i < 1250; i += T) df[i] = __ldg(af + i);
-      for (int i = tid; i < 2000; i += T) db[i] = __ldg(ab + i);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fa[k] = (tid + k * T < 1250) ? __ldg(af + tid + k * T) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fb[k] = (tid + k * T < 2000) ? __ldg(ab + tid + k * T) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4* __restrict__ P4w2 = reinterpret_cast<const float4*>(P + W2);
     float4 v[3];
@@ -112,6 +113,14 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     if (tid < 250) s.w1[tid] = w1v;
     if (tid < 500) s.w4[tid] = w4v;
     if (tid < 10) s.b1[tid] = bv; else if (tid < 20) s.b4[tid - 10] = bv; else if (tid < 40) s.b2[tid - 20] = bv;
+    if (fast) {
+      float4* df = reinterpret_cast<float4*>(s.w2f);
+      float4* db = reinterpret_cast<float4*>(s.w2b);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) if (tid + k * T < 1250) df[tid + k * T] = fa[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (tid + k * T < 2000) db[tid + k * T] = fb[k];
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i4 = tid + k * T;
@@ -246,33 +255,32 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     }
     cl.sync();                                     // (2) p2 / a2 complete everywhere
 
-    // -------------------------------------------------------------- S3: fc1 rows of this CTA (16 lanes per output), broadcast
+    // -------------------------------------------------------------- S3: fc1 + relu + dropout (redundant in every CTA:
+    //                                                                 16 k MACs cost less than a broadcast + cluster barrier)
     {
-      const int jl = tid >> 4, l16 = tid & 15, j = cr * K::FC1_PER + jl;
-      const bool act = jl < K::FC1_PER && j < 50;
+      const int j = tid >> 3, l8 = tid & 7;
       float sum = 0.f;
-      if (act) {
+      if (j < 50) {
         const float4* wrow = reinterpret_cast<const float4*>(P + W3 + j * 320);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const float4 w = __ldg(wrow + l16 + 16 * k);
-          const float4 vv = *reinterpret_cast<const float4*>(&s.p2[(l16 + 16 * k) * 4]);
+        for (int k = 0; k < 10; ++k) {
+          const float4 w = __ldg(wrow + l8 + 8 * k);
+          const float4 vv = *reinterpret_cast<const float4*>(&s.p2[(l8 + 8 * k) * 4]);
           sum = fmaf(w.x, vv.x, sum); sum = fmaf(w.y, vv.y, sum);
           sum = fmaf(w.z, vv.z, sum); sum = fmaf(w.w, vv.w, sum);
         }
       }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 8);
       sum += __shfl_xor_sync(0xffffffffu, sum, 4);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      if (act && l16 == 0) {
+      if (j < 50 && l8 == 0) {
         const float pre = sum + __ldg(P + B3 + j);
         const float dm = a.training ? (s.rnd[20 + j] >= a.p_drop ? keep_scale : 0.f) : 1.f;
-        bcast<C>(cl, &s.h[j], fmaxf(pre, 0.f) * dm);
-        bcast<C>(cl, &s.hm[j], pre > 0.f ? dm : 0.f);
+        s.h[j] = fmaxf(pre, 0.f) * dm;
+        s.hm[j] = pre > 0.f ? dm : 0.f;
       }
     }
-    cl.sync();                                     // (3) h / hm complete everywhere
+    __syncthreads();
 
     // -------------------------------------------------------------- S4: fc2 + log_softmax + nll (redundant in every CTA)
     if (tid < 32) {
@@ -309,7 +317,10 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       else if (tid < 70) a.mask_out[(size_t)b * 70 + tid] = a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
     }
     __syncthreads();
-    if (!a.backward) { cl.sync(); continue; }      // keep the cluster in lock-step before buffers are reused
+    if (!a.backward) {                             // keep the cluster in lock-step before buffers are reused
+      if (b + n_clusters < a.B) cl.sync();
+      continue;
+    }
 
     // -------------------------------------------------------------- S5: fc2 backward (weight slice of this CTA; dh everywhere)
     if (tid < K::W4_PER) {
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
         if (k == 0) s.g[B1 + out / 25] += gsum;
       }
     }
-    cl.sync();                                     // (6) nobody still reads buffers the next sample's broadcasts overwrite
+    if (b + n_clusters < a.B) cl.sync();           // (6) nobody still reads buffers the next sample's broadcasts overwrite
   }
 
   // ------------------------------------------------------------------ flush: only the gradient slices this CTA owns

@@ -37,11 +37,11 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
 
 # ---- phase summary (markers: comment lines containing '-- P0:' / '-- S1:' etc.)
 import os
-src = [p for p in ("dist_tuto.pth_b200/csrc/" + k[0] for k in agg if k[0].endswith(".cu")) if os.path.isfile(p)]
+src = sorted({p for p in ("dist_tuto.pth_b200/csrc/" + k[0] for k in agg if k[0].endswith(".cu")) if os.path.isfile(p)}, key=lambda p: -sum(v[1] for k, v in agg.items() if p.endswith(k[0])))
 if src:
     marks = []
     for n, ln in enumerate(open(src[0]), 1):
-        m = re.search(r"// -+ ((?:P|S)\w+):? (.*)", ln)
+        m = re.search(r"// -+ ((?:P|S)[\w/]+):? (.*)", ln)
         if m:
             marks.append((n, m.group(1) + " " + m.group(2)[:40]))
         elif "// ---" in ln and "flush" in ln:
