@@ -39,13 +39,12 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   __shared__ unsigned int s_par;
   pdl_wait();                        // gradients of this step (previous kernel) are complete and visible
   pdl_launch_dependents();           // the next step's forward/backward kernel may pre-launch now (it zeroes its smem, then waits)
+  unsigned long long st = 0ull;
+  unsigned int seen = 0u;
   if (threadIdx.x == 0) {
-    unsigned long long st = a.step != nullptr ? *reinterpret_cast<volatile unsigned long long*>(a.step) : 0ull;
+    st = a.step != nullptr ? *reinterpret_cast<volatile unsigned long long*>(a.step) : 0ull;
     s_par = (unsigned int)(st & 1ull);
-    if (a.step != nullptr) {
-      const unsigned int seen = atomicAdd(a.done_counter, 1u);
-      if (seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
-    }
+    if (a.step != nullptr) seen = atomicAdd(a.done_counter, 1u);    // result is only consumed at the very end (latency hidden)
   }
   __syncthreads();
   uint32_t epoch = 0;
@@ -104,6 +103,8 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
     }
   }
   if (world > 1 && threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
+  // the last block to have checked in knows every block has read the step counter: it publishes step + 1
+  if (threadIdx.x == 0 && a.step != nullptr && seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
 }
 
 // Plain flat momentum SGD (generic models: gradients already averaged in `grad`)
