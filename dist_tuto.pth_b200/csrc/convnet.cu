@@ -56,7 +56,7 @@ struct __align__(1024) Smem {
   float w4[500];
   float b4[12];
   float x[784];
-  float p1[1440];           // relu(pool(conv1))  [10][12][12]
+  float p1[P1_SIZE];        // relu(pool(conv1))  [10][12][12], padded strides (see convnet_args.cuh)
   float p2[320];            // relu(pool(drop(conv2)))  [20][4][4]
   float g2[320];            // gradient at the pooled conv2 argmax
   float2 g1[1440];          // (gradient at the pooled conv1 argmax, input offset of that position as int bits)
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       // zero the bf16 operand tiles (row / K padding must be 0), build the im2col LUT, set up mbarrier + TMEM
       uint4* z = reinterpret_cast<uint4*>(s.u.tc.Bw);
       for (int i = tid; i < (16384 + 32768) / 16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (tid < 256) s.koff[tid] = tid < 250 ? (short)((tid / 25) * 144 + ((tid % 25) / 5) * 12 + (tid % 5)) : (short)-1;
+      if (tid < 256) s.koff[tid] = tid < 250 ? (short)p1_idx(tid / 25, (tid % 25) / 5, tid % 5) : (short)-1;
       if (tid == 0) { tc::mbar_init(reinterpret_cast<uint64_t*>(&s.mma_bar), 1); tc::mbar_fence_init(); }
       if ((tid >> 5) == 1) tc::tmem_alloc<512>(&s.tmem_slot);
       __syncthreads();
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       if (a01 > m) { m = a01; arg = 1; }
       if (a10 > m) { m = a10; arg = 2; }
       if (a11 > m) { m = a11; arg = 3; }
-      s.p1[o] = fmaxf(m, 0.f);
+      s.p1[p1_idx(c, py, px)] = fmaxf(m, 0.f);
       s.a1[o] = (unsigned char)arg;
     }
     if (tid < 20)
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int chunk = tid + m * T, r = chunk >> 5, c = chunk & 31;
-        const int base = (r >> 3) * 12 + (r & 7);
+        const int base = (r >> 3) * P1_ROW + (r & 7);
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -288,11 +288,11 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
       for (int ci = ci0; ci < ci1; ++ci) {
         float patch[6][6];
-        const float* src = &s.p1[ci * 144 + (2 * py) * 12 + 2 * px];
+        const float* src = &s.p1[p1_idx(ci, 2 * py, 2 * px)];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) patch[i][j] = src[i * 12 + j];
+          for (int j = 0; j < 6; ++j) patch[i][j] = src[i * P1_ROW + j];
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
               if (gv != 0.f) {
                 const int arg = s.a2[co * 16 + cell];
                 const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
-                const float* src = &s.p1[ci * 144 + (ay + ky) * 12 + ax];
+                const float* src = &s.p1[p1_idx(ci, ay + ky, ax)];
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) acc[kx] = fmaf(gv, src[kx], acc[kx]);
               }
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
         const int ko = s.koff[k];
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
         if (ko >= 0) {
-          const float* src = &s.p1[ko + oy * 12];
+          const float* src = &s.p1[ko + oy * P1_ROW];
           pk = make_uint4(b2::pack_bf16x2(src[0], src[1]), b2::pack_bf16x2(src[2], src[3]), b2::pack_bf16x2(src[4], src[5]),
                           b2::pack_bf16x2(src[6], src[7]));
         }
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
           }
           const int o = (half * 5 + cil) * 144 + rem, arg = s.a1[o];
           const int off = (2 * y + (arg >> 1)) * 28 + 2 * x + (arg & 1);
-          s.g1[o] = make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off));
+          s.g1[o] = make_float2(s.p1[p1_of(o)] > 0.f ? d : 0.f, __int_as_float(off));
         }
         __syncthreads();
       }
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       for (int ks = 0; ks < 6; ++ks) d += s.u.simt.part[ks * 1440 + o];
       const int cell = o % 144, arg = s.a1[o];
       const int off = (2 * (cell / 12) + (arg >> 1)) * 28 + 2 * (cell % 12) + (arg & 1);
-      s.g1[o] = make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off));
+      s.g1[o] = make_float2(s.p1[p1_of(o)] > 0.f ? d : 0.f, __int_as_float(off));
     }
     __syncthreads();
     }

@@ -35,4 +35,11 @@ struct Args {
 
 constexpr int AUX_W2F = 0, AUX_W2B = 5000, AUX_TOTAL = 13000;
 
+// relu(pool(conv1)) lives in shared memory as [10 planes][12 rows][12 cols] with row stride 13 and plane stride 161: with these
+// strides the 32 (input channel, kernel row) work items of a warp in the conv2 weight-gradient phase hit 32 distinct banks
+// (dense 12/144 strides gave 4.8-way conflicts there -- 41 % of all excess shared-memory wavefronts of the kernel).
+constexpr int P1_ROW = 13, P1_PLANE = 161, P1_SIZE = (10 * P1_PLANE + 3) / 4 * 4;   // keeps the next shared array 16-byte aligned
+__host__ __device__ constexpr int p1_idx(int c, int y, int x) { return c * P1_PLANE + y * P1_ROW + x; }
+__host__ __device__ constexpr int p1_of(int o) { return (o / 144) * P1_PLANE + ((o % 144) / 12) * P1_ROW + (o % 12); }   // o = c*144 + y*12 + x
+
 }  // namespace cn

@@ -46,7 +46,7 @@ struct __align__(16) Smem {
   float w2f[250 * 20];      // [ci][ky][kx][co]
   float w2b[500 * 16];      // [co][ky][kx][half][8]
   float x[784];
-  float p1[1440];
+  float p1[P1_SIZE];        // padded strides, see convnet_args.cuh
   float p2[320];
   float g2[320];
   float2 g1[1440];
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       if (a01 > m) { m = a01; arg = 1; }
       if (a10 > m) { m = a10; arg = 2; }
       if (a11 > m) { m = a11; arg = 3; }
-      bcast<C>(cl, &s.p1[o], fmaxf(m, 0.f));
+      bcast<C>(cl, &s.p1[p1_idx(c, py, px)], fmaxf(m, 0.f));
       bcast<C>(cl, &s.a1[o], (unsigned char)arg);
     }
     cl.sync();                                     // (1) p1 / a1 complete everywhere
@@ -208,11 +208,11 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
       float patch[6][6];
-      const float* src = &s.p1[ci * 144 + (2 * py) * 12 + 2 * px];
+      const float* src = &s.p1[p1_idx(ci, 2 * py, 2 * px)];
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) patch[i][j] = src[i * 12 + j];
+        for (int j = 0; j < 6; ++j) patch[i][j] = src[i * P1_ROW + j];
 #pragma unroll
       for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
         const float gv = s.g2[co * 16 + cell];
         const int arg = s.a2[co * 16 + cell];
         const int ay = 2 * (cell >> 2) + (arg >> 1), ax = 2 * (cell & 3) + (arg & 1);
-        acc = fmaf(gv, s.p1[ci * 144 + (ay + ky) * 12 + ax + kx], acc);
+        acc = fmaf(gv, s.p1[p1_idx(ci, ay + ky, ax + kx)], acc);
       }
       s.g[W2 + e] += acc;
     }
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       const int y = 2 * (tile / 6) + (p >> 1), x = 2 * (tile % 6) + (p & 1);
       const int o = (half * 5 + c) * 144 + y * 12 + x, arg = s.a1[o];
       const int off = (2 * y + (arg >> 1)) * 28 + 2 * x + (arg & 1);
-      bcast<C>(cl, &s.g1[o], make_float2(s.p1[o] > 0.f ? d : 0.f, __int_as_float(off)));
+      bcast<C>(cl, &s.g1[o], make_float2(s.p1[p1_of(o)] > 0.f ? d : 0.f, __int_as_float(off)));
     }
     cl.sync();                                     // (5) g1 complete everywhere
 
