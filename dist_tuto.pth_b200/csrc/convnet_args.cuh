@@ -39,6 +39,9 @@ constexpr int AUX_W2F = 0, AUX_W2B = 5000, AUX_TOTAL = 13000;
 // strides the 32 (input channel, kernel row) work items of a warp in the conv2 weight-gradient phase hit 32 distinct banks
 // (dense 12/144 strides gave 4.8-way conflicts there -- 41 % of all excess shared-memory wavefronts of the kernel).
 constexpr int P1_ROW = 13, P1_PLANE = 161, P1_SIZE = (10 * P1_PLANE + 3) / 4 * 4;   // keeps the next shared array 16-byte aligned
+// The zero-padded conv2-output gradient [20][16][16] uses row stride 20 / plane stride 324 and is read as float2 pairs:
+// 9720 -> 3240 shared-memory wavefronts per sample in the conv2 data-gradient phase (dense 16/256 strides, scalar loads).
+constexpr int DC_ROW = 20, DC_PLANE = 324, DC_SIZE = 20 * DC_PLANE;
 __host__ __device__ constexpr int p1_idx(int c, int y, int x) { return c * P1_PLANE + y * P1_ROW + x; }
 __host__ __device__ constexpr int p1_of(int o) { return (o / 144) * P1_PLANE + ((o % 144) / 12) * P1_ROW + (o % 12); }   // o = c*144 + y*12 + x
 

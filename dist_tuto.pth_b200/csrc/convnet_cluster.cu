@@ -57,7 +57,7 @@ struct __align__(16) Smem {
   float m2[20];
   float rnd[72];
   float part[7200];         // conv2 split-K partials / dgrad split-K partials
-  float dc2pad[20 * 256];
+  float dc2pad[DC_SIZE];   
   float g[NPAR];
   unsigned char a1[1440];
   unsigned char a2[320];
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       s.rnd[q * 4 + 0] = r.x * k; s.rnd[q * 4 + 1] = r.y * k;
       s.rnd[q * 4 + 2] = r.z * k; s.rnd[q * 4 + 3] = r.w * k;
     }
-    for (int i = tid; i < 20 * 256 / 4; i += T) reinterpret_cast<float4*>(s.dc2pad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < DC_SIZE / 4; i += T) reinterpret_cast<float4*>(s.dc2pad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (tid < 20) s.m2[tid] = a.training ? (s.rnd[tid] >= a.p_drop ? keep_scale : 0.f) : 1.f;
 
@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) patch[i][j] = s.x[(2 * py + i) * 28 + 2 * px + j];
+        for (int j = 0; j < 3; ++j) {              // 8-byte aligned pairs: 18 LDS.64 instead of 36 LDS.32
+          const float2 q = *reinterpret_cast<const float2*>(&s.x[(2 * py + i) * 28 + 2 * px + 2 * j]);
+          patch[i][2 * j] = q.x; patch[i][2 * j + 1] = q.y;
+        }
       const float bias = s.b1[c];
       float a00 = bias, a01 = bias, a10 = bias, a11 = bias;
 #pragma unroll
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     for (int o = tid; o < 320; o += T) {            // zero-padded conv2-output gradient (every CTA builds its own copy)
       const int co = o >> 4, cell = o & 15, arg = s.a2[o];
       const int y = 2 * (cell >> 2) + (arg >> 1), x = 2 * (cell & 3) + (arg & 1);
-      s.dc2pad[co * 256 + (y + 4) * 16 + (x + 4)] = s.g2[o];
+      s.dc2pad[co * DC_PLANE + (y + 4) * DC_ROW + (x + 4)] = s.g2[o];
     }
     // weight gradient: 5000 / C entries (co, ci, ky, kx), 16 pooled cells each
     for (int l = tid; l < K::W2_PER; l += T) {
@@ -415,11 +418,14 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       for (int co = ks * CO_PER; co < (ks + 1) * CO_PER; ++co) {
         if (s.m2[co] == 0.f) continue;
         float patch[6][6];
-        const float* src = &s.dc2pad[co * 256 + y0 * 16 + x0];
+        const float2* src = reinterpret_cast<const float2*>(&s.dc2pad[co * DC_PLANE + y0 * DC_ROW + x0]);   // even offsets
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) patch[i][j] = src[i * 16 + j];
+          for (int j = 0; j < 3; ++j) {
+            const float2 q = src[i * (DC_ROW / 2) + j];
+            patch[i][2 * j] = q.x; patch[i][2 * j + 1] = q.y;
+          }
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll

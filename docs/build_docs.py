@@ -1,10 +1,12 @@
 """Docs toolchain (counterpart of the reference Makefile `all` target, which called an external paperify.py):
-renders docs/tutorial.md to a standalone docs/tutorial.html with no external dependency."""
+renders docs/tutorial.md to a standalone docs/tutorial.html with no external dependency, and (re)draws docs/figs/*.svg."""
+import sys
 import html
 import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
 
 
 def render(md: str) -> str:
@@ -48,12 +50,16 @@ def render(md: str) -> str:
 
 def inline(t: str) -> str:
     t = html.escape(t)
+    t = re.sub(r"!\[([^\]]*)\]\(([^)]+)\)", r'<img alt="\1" src="\2" style="max-width:100%">', t)
     t = re.sub(r"`([^`]+)`", r"<code>\1</code>", t)
     t = re.sub(r"\*\*([^*]+)\*\*", r"<b>\1</b>", t)
     return re.sub(r"\*([^*]+)\*", r"<i>\1</i>", t)
 
 
 if __name__ == "__main__":
+    import make_figs   # docs/figs/*.svg (the reference ships its diagrams as binaries under figs/; ours are generated)
+
+    make_figs.make_all()
     src = open(os.path.join(HERE, "tutorial.md")).read()
     open(os.path.join(HERE, "tutorial.html"), "w").write(render(src))
     print("wrote docs/tutorial.html")
