@@ -32,13 +32,15 @@ def run_mode(mode, rank, size, dev):
     ddp = None
     if mode == "ours":
         ddp = DistributedDataParallel(model, bucket_cap_bytes=ARGS.bucket_mb << 20)
+        if getattr(ARGS, "flat_sgd", True):     # one sgd_flat launch per bucket (update + re-zero), params become views
+            opt = b2.FlatSGD(ddp, lr=0.01, momentum=0.5)
     B = ARGS.batch
     x = torch.randn(B, 3, ARGS.res, ARGS.res, device=dev).to(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (B,), device=dev)
 
     def step():
         if ddp is not None:
-            ddp.zero_grad()
+            opt.zero_grad() if isinstance(opt, b2.FlatSGD) else ddp.zero_grad()
         else:
             opt.zero_grad(set_to_none=False)
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -95,6 +97,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--bucket-mb", type=int, default=8)
+    ap.add_argument("--no-flat-sgd", dest="flat_sgd", action="store_false", help="torch.optim.SGD instead of FlatSGD on our arm")
     ap.add_argument("--out", default=None)
     ARGS = ap.parse_args()
     ARGS.out = ARGS.out or f"gpurun_out/resnet_{ARGS.gpus}.json"

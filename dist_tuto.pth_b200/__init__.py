@@ -11,6 +11,7 @@ Public surface (tutorial names kept; see each module for file:line parity):
     Partition DataPartitioner partition_dataset         data.py
     Net                                                 models/convnet.py
     average_gradients GradBucket DistributedDataParallel parallel/ddp.py
+    FlatSGD (one-launch momentum SGD over flat buffers) ops/optim.py
     run / train / TrainConfig                           train.py
 """
 from .comm import (reduce_op, ReduceOp, send, recv, isend, irecv, broadcast, reduce, all_reduce,  # noqa: F401
@@ -24,6 +25,7 @@ from .data import (Partition, DataPartitioner, partition_dataset, SyntheticMNIST
 from .models.convnet import Net  # noqa: F401
 from .parallel.ddp import (average_gradients, GradBucket, DistributedDataParallel,  # noqa: F401
                            broadcast_parameters)
+from .ops.optim import FlatSGD  # noqa: F401
 from .train import run, train, TrainConfig  # noqa: F401
 
 __version__ = "0.1.0"
