@@ -24,11 +24,11 @@ from typing import Callable, Optional
 
 import torch
 import torch.nn.functional as F
-import torch.optim as optim
 
 from . import comm
 from .data import partition_dataset
 from .models.convnet import Net
+from .ops.optim import FlatSGD
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
 __all__ = ["run", "train", "TrainConfig"]
@@ -81,13 +81,14 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
             model.load_state_dict(torch.load(cfg.resume, map_location="cpu")["model"])
         broadcast_parameters(model)
         model._grad_bucket = GradBucket(list(model.parameters()))
-        optimizer = optim.SGD(model.parameters(), lr=cfg.lr, momentum=cfg.momentum)
+        # optim.SGD(lr=0.01, momentum=0.5) of train_dist.py:110, over flat buffers: update + zero_grad in one pass
+        optimizer = FlatSGD(model, lr=cfg.lr, momentum=cfg.momentum)
         acc = torch.zeros((), device=device)
 
         def step_fn(data, target):
             data = data.to(device, non_blocking=True)
             target = target.to(device, non_blocking=True)
-            model._grad_bucket.zero_()                           # optimizer.zero_grad()
+            optimizer.zero_grad()                                # buckets were re-zeroed by the previous step()
             output = model(data)
             loss = F.nll_loss(output, target)
             acc.add_(loss.detach())                              # epoch_loss += loss (D4 fixed)
