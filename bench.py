@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--ref-avg", default="tutorial", choices=["tutorial", "committed"])
     ap.add_argument("--graph-chunk", type=int, default=50)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--loader-buffers", type=int, default=6, help="pinned ring depth of the native loader (e2e arm)")
     return ap.parse_args()
 
 
@@ -98,9 +99,10 @@ def ours(args):
 
         # ------------------------------------------------------------ e2e: public API, pinned H2D + loss D2H per step
         e2e, h2d = None, bsz * 784 * 1 + bsz * 8          # raw uint8 pixels (normalised in-kernel) + int64 labels
+        exec_chunk = 1
         if not args.no_e2e:
             ds = SyntheticMNIST(n=60000, seed=1234)
-            loader, bsz2 = b2.partition_dataset(ds, raw_uint8=True)
+            loader, bsz2 = b2.partition_dataset(ds, raw_uint8=True, num_buffers=args.loader_buffers)
             assert bsz2 == bsz
 
             # the call a user makes (train.py does exactly this per epoch): the C++ executor drives
@@ -117,6 +119,8 @@ def ours(args):
                 d, _ = tr.run_native(loader, max_steps=K - done)
                 done += d
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
+            ex = tr._executors[id(loader)][0]
+            exec_chunk = int(os.environ.get("B200DIST_EXEC_CHUNK", "1")) if ex.chunking() else 1
             torch.cuda.synchronize()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
             e2e = bsz * size * K / (e2e_ms / 1e3)
@@ -130,8 +134,10 @@ def ours(args):
                                             "cluster_ctas_per_sample": tr.cluster,
                                             "l2": f"inputs cycle through a {pool * batch_bytes >> 20} MB device pool (> 126 MB L2)",
                                             "graph_chunk": G, "symm": sym,
-                                            "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor (one cudaGraphLaunch "
-                                                        "per step: H2D uint8 batch + labels, 2 kernels, D2H loss)"}), flush=True)
+                                            "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
+                                                        "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "
+                                                        + (f"{exec_chunk} steps per cudaGraphLaunch" if exec_chunk > 1 else "one cudaGraphLaunch per step")}),
+                  flush=True)
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

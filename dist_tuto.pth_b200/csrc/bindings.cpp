@@ -143,13 +143,15 @@ struct ExecutorPy {
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
-             int max_in_flight, int cluster, torch::Tensor aux)
+             int max_in_flight, int cluster, torch::Tensor aux, int chunk)
       : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
     const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
-    TORCH_CHECK(in_dev.is_cuda() && in_dev.scalar_type() == torch::kUInt8 && (size_t)in_dev.numel() >= 2 * block,
-                "in_dev: CUDA uint8 buffer of >= 2 * block bytes");
+    chunk = std::max(1, std::min(chunk, 8));
+    const size_t nblk = (size_t)std::max(2, chunk);
+    TORCH_CHECK(in_dev.is_cuda() && in_dev.scalar_type() == torch::kUInt8 && (size_t)in_dev.numel() >= nblk * block,
+                "in_dev: CUDA uint8 buffer of >= max(2, chunk) * block bytes");
     b2::StepConfig c;
     std::memset(&c, 0, sizeof(c));
     c.params = params.data_ptr<float>(); c.momentum = momentum.data_ptr<float>(); c.grads_local = grads.data_ptr<float>();
@@ -158,7 +160,8 @@ struct ExecutorPy {
     c.step_counter = reinterpret_cast<unsigned long long*>(step.data_ptr());
     c.done_counter = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
     c.loss_acc = loss_acc.data_ptr<float>();
-    c.in_dev[0] = in_dev.data_ptr<uint8_t>(); c.in_dev[1] = in_dev.data_ptr<uint8_t>() + block;
+    for (size_t i = 0; i < nblk; ++i) c.in_dev[i] = in_dev.data_ptr<uint8_t>() + i * block;
+    c.chunk = chunk;
     c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
     c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;
     c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop; c.cluster = cluster;
@@ -332,12 +335,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<ExecutorPy>(m, "StepExecutor")
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
-                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor>(),
+                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
-           py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::keep_alive<1, 2>())
+           py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::arg("chunk") = 1,
+           py::keep_alive<1, 2>())
+      .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
+      .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
       .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
       .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });

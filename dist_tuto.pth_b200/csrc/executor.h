@@ -20,7 +20,9 @@ struct StepConfig {
   unsigned long long* step_counter;
   unsigned int* done_counter;
   float* loss_acc;                   // [2]
-  unsigned char* in_dev[2];          // double-buffered device input blocks, same layout as a loader slot: [x | pad | y]
+  unsigned char* in_dev[8];          // device input blocks, same layout as a loader slot: [x | pad | y]; [0..1] double-buffer
+                                     // the per-step path, [0..chunk) are the blocks of a chunk graph
+  int chunk;                         // steps per chunk graph (0/1 = per-step launches only), <= 8
   int B, x_u8, training, rank, world, cluster;
   unsigned long long seed;
   long long sample_base, grad_stride;
@@ -39,6 +41,8 @@ class StepExecutor {
   void drain();                      // wait for everything in flight, release loader slots
   double last_loss_cumulative() const { return last_loss_; }
   const std::string& error() const { return err_; }
+  bool chunking() const { return chunk_ok_; }
+  const std::string& chunk_note() const { return chunk_note_; }   // why chunk graphs were turned off (if they were)
 
  private:
   struct Slot {
@@ -46,6 +50,8 @@ class StepExecutor {
     float* loss_pin = nullptr;
   };
   bool capture(int parity);
+  bool capture_chunk(int group);
+  void record_step(const void* x, const long long* y);
   void retire_oldest();
   StepConfig cfg_;
   NativeLoader* loader_;
@@ -54,10 +60,16 @@ class StepExecutor {
   cudaGraphExec_t exec_[2] = {nullptr, nullptr};     // the two kernels, reading in_dev[parity]
   cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr};
   std::vector<Slot> slots_;
-  std::deque<int> in_flight_;
+  // chunk graphs: K consecutive steps (K H2D copies, 2K kernels, K loss read-backs) as ONE graph launch; one graph per
+  // group of K loader slots (the slot of batch b is b % num_slots, so the pinned addresses of a group are fixed)
+  std::vector<cudaGraphExec_t> chunk_exec_;
+  std::vector<cudaEvent_t> chunk_ev_;  // capture-time fork/join events
+  bool chunk_ok_ = false;
+  struct Flight { int slot, ev_slot; };
+  std::deque<Flight> in_flight_;
   int64_t issued_ = 0;
   double last_loss_ = 0.0;
-  std::string err_;
+  std::string err_, chunk_note_;
 };
 
 }  // namespace b2

@@ -19,6 +19,7 @@ interchange with ``models.convnet.Net``).
 """
 from __future__ import annotations
 
+import os
 from collections import deque
 from typing import Dict, Optional
 
@@ -68,7 +69,6 @@ def pick_cluster(bsz: int) -> int:
     a shorter per-sample latency (csrc/convnet_cluster.cu): 32.8 us (1 CTA) -> 28.7 (2) -> 24.6 (4).  Clusters of 8
     only fit two per GPC with this kernel's 216 KB of shared memory per CTA, so 16 of them do not fit in one wave (46 us);
     they are used only when the batch is <= 8.  ``B200DIST_CONVNET_CLUSTER`` overrides."""
-    import os
     env = os.environ.get("B200DIST_CONVNET_CLUSTER")
     if env is not None:
         return int(env)
@@ -302,12 +302,17 @@ class FusedTrainer:
             if loader.batch_size != self.bsz:
                 raise ValueError("loader batch size != trainer batch size")
             block = (int(loader._l.block_bytes()) + 255) // 256 * 256
-            in_dev = torch.zeros(2 * block, dtype=torch.uint8, device=self.device)
+            # B200DIST_EXEC_CHUNK=K: K steps per graph launch when the loader ring allows it (num_buffers % K == 0, >= 2K),
+            # see executor.cpp.  Off by default: measured on B200 (profiles/executor_chunk_graphs.json) the per-step
+            # H2D -> kernel edge keeps the programmatic-dependent-launch overlap from forming inside the chunk, so a
+            # chunk costs as much per step as single-step graphs plus a ~20 us bubble between chunks.
+            chunk = max(1, min(8, int(os.environ.get("B200DIST_EXEC_CHUNK", "1"))))
+            in_dev = torch.zeros(max(2, chunk) * block, dtype=torch.uint8, device=self.device)
             ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
-                                      self.cluster, self.aux),
+                                      self.cluster, self.aux, chunk),
                   self.training)
             self._executors[id(loader)] = ex
         if new_epoch:

@@ -193,27 +193,39 @@ def test_train_loop_single_gpu_fused(dev):
     assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
 
 
-def test_native_executor_matches_python_loop(dev):
-    """C++ StepExecutor (prefetch thread -> graph launches) == stepping the same loader from Python."""
+@pytest.mark.parametrize("num_buffers,chunk", [(6, 4), (8, 4), (8, 2), (12, 4)])
+def test_native_executor_matches_python_loop(dev, num_buffers, chunk, monkeypatch):
+    """C++ StepExecutor (prefetch thread -> graph launches) == stepping the same loader from Python.
+    (6, 4): ring too shallow -> per-step graphs; the others: K-step chunk graphs + per-step tail."""
+    monkeypatch.setenv("B200DIST_EXEC_CHUNK", str(chunk))
     from dist_tuto.pth_b200 import data as D
     from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
     ds = D.SyntheticMNIST(n=1000, seed=2)                 # 1000 = 15 x 64 + 40 -> exercises the short tail batch
     part = D.Partition(ds, list(range(1000)))
     res = []
     for native in (True, False):
-        loader = D.NativeBatchLoader(part, 64, seed=9, raw_uint8=True, pin_memory=True)
+        loader = D.NativeBatchLoader(part, 64, seed=9, raw_uint8=True, pin_memory=True, num_buffers=num_buffers)
         tr = FusedTrainer(64, lr=0.05, seed=3, device=dev, p_drop=0.5, raw_uint8=True)
         if native:
             done, finished = tr.run_native(loader)
             assert done == 16 and finished
+            ex = tr._executors[id(loader)][0]
+            assert ex.chunking() == (num_buffers % chunk == 0 and num_buffers >= 2 * chunk), ex.chunk_note()
+            done2, _ = tr.run_native(loader, max_steps=6)        # second epoch, budgeted: chunk (4) + 2 single steps
+            assert done2 == 6
         else:
             n = 0
             for x, y in loader:
                 tr.step(x, y)
                 n += 1
             assert n == 16
+            for i, (x, y) in enumerate(loader):
+                if i == 6:
+                    break
+                tr.step(x, y)
+        torch.cuda.synchronize()                          # the python loop's last steps are still in flight on tr.stream
         res.append((tr.params.clone(), tr.pop_loss_sum(), int(tr.step_counter.item())))
-    assert res[0][2] == res[1][2] == 16
+    assert res[0][2] == res[1][2] == 22
     assert abs(res[0][1] - res[1][1]) < 1e-3 * abs(res[1][1])
     assert torch.allclose(res[0][0], res[1][0], atol=1e-5, rtol=1e-4)
 
