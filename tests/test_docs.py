@@ -1,0 +1,31 @@
+"""Docs toolchain (reference Makefile `all` target): figures are well-formed SVG, the tutorial renders with them."""
+import os
+import sys
+import xml.dom.minidom
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "docs"))
+
+
+def test_figures_are_wellformed_svg(tmp_path, monkeypatch):
+    import make_figs
+    monkeypatch.setattr(make_figs, "OUT", str(tmp_path))
+    paths = make_figs.make_all()
+    names = {os.path.basename(p) for p in paths}
+    # the reference's figs/ set (send_recv, broadcast, scatter, gather, reduce, all_reduce, all_gather) + ours
+    for want in ("send_recv", "broadcast", "scatter", "gather", "reduce", "all_reduce", "all_gather", "ring_allreduce",
+                 "peer_allreduce", "fused_step"):
+        assert want + ".svg" in names
+    for p in paths:
+        doc = xml.dom.minidom.parse(p)
+        assert doc.documentElement.tagName == "svg"
+
+
+def test_tutorial_renders_with_figures():
+    import build_docs
+    md = open(os.path.join(ROOT, "docs", "tutorial.md")).read()
+    html = build_docs.render(md)
+    assert html.count("<img") >= 10 and "<h2>" in html and "<pre>" in html
+    for sec in ("Setup", "Point-to-Point Communication", "Collective Communication", "Distributed Training",
+                "Our Own Ring-Allreduce", "Communication Backends", "Initialization Methods"):
+        assert sec in html          # the section structure of tuto.md
