@@ -42,7 +42,8 @@ int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const Signa
 int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t stream);
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream);
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
+                            const PeerPtrs* inbox, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -143,7 +144,7 @@ struct ExecutorPy {
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
-             int max_in_flight, int cluster, torch::Tensor aux, int chunk)
+             int max_in_flight, int cluster, torch::Tensor aux, int chunk, std::vector<unsigned long long> inbox)
       : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
@@ -167,6 +168,9 @@ struct ExecutorPy {
     c.lr = (float)lr; c.mu = (float)mu; c.p_drop = (float)p_drop; c.cluster = cluster;
     TORCH_CHECK(aux.is_cuda() && aux.scalar_type() == torch::kFloat32 && aux.numel() >= 13000, "aux: CUDA fp32 [13000]");
     c.aux = aux.data_ptr<float>();
+    TORCH_CHECK(inbox.empty() || (int)inbox.size() == world, "inbox: one pointer per rank (or none)");
+    for (size_t i = 0; i < inbox.size() && i < 8; ++i) c.inbox_ptrs[i] = (void*)(uintptr_t)inbox[i];
+    c.push = !inbox.empty();
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
     impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
@@ -236,8 +240,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_sgd", [](std::vector<unsigned long long> grads, std::vector<unsigned long long> sigs, torch::Tensor params,
                             torch::Tensor momentum, c10::optional<torch::Tensor> step, double lr, double mu, double scale,
                             int rank, int world, bool zero_grads, int64_t grad_stride, c10::optional<torch::Tensor> done_counter,
-                            c10::optional<torch::Tensor> aux) {
+                            c10::optional<torch::Tensor> aux, std::vector<unsigned long long> inbox) {
     check_cuda_contig(params, "params"); check_cuda_contig(momentum, "momentum");
+    TORCH_CHECK(inbox.empty() || (int)inbox.size() == world, "inbox: one pointer per rank (or none)");
+    PeerPtrs ib = to_ptrs(inbox);
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && momentum.scalar_type() == torch::kFloat32, "fp32 flat buffers");
     TORCH_CHECK(params.numel() % 4 == 0 && params.numel() == momentum.numel(), "flat buffers must be padded to 4 elements");
     PeerPtrs g = to_ptrs(grads); SignalPadsH s = to_sig(sigs);
@@ -248,11 +254,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (aux.has_value()) { TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == torch::kFloat32 && aux->numel() >= 13000); ax = aux->data_ptr<float>(); }
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
-                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax, cur_stream()),
+                                    (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax,
+                                    inbox.empty() ? nullptr : &ib, cur_stream()),
             "allreduce_sgd launch");
   }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
      py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
-     py::arg("done_counter") = py::none(), py::arg("aux") = py::none());
+     py::arg("done_counter") = py::none(), py::arg("aux") = py::none(), py::arg("inbox") = std::vector<unsigned long long>());
   m.def("sgd_flat", [](torch::Tensor p, torch::Tensor mom, torch::Tensor g, double lr, double mu, double wd, bool zero_grad) {
     check_cuda_contig(p, "p"); check_cuda_contig(mom, "m"); check_cuda_contig(g, "g");
     TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
@@ -335,13 +342,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<ExecutorPy>(m, "StepExecutor")
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
-                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int>(),
+                    int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int,
+                    std::vector<unsigned long long>>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
            py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::arg("chunk") = 1,
-           py::keep_alive<1, 2>())
+           py::arg("inbox") = std::vector<unsigned long long>(), py::keep_alive<1, 2>())
       .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
       .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)

@@ -57,6 +57,19 @@ __device__ __forceinline__ void st_cg_v4(void* p, uint4 v) {
                : "memory");
 }
 
+// 16-byte volatile accesses for flag-in-data ("LL") exchanges: one store / one load instruction per line, never cached in
+// L1, so a line that crossed NVLink is observed old or new per 8-byte half (the reader checks both flags)
+__device__ __forceinline__ void st_volatile_v4(void* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 // NVLS: in-switch reduction / broadcast on a multicast address (SASS: LDGMC / STGMC... )
 __device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const void* mc) {
   float4 r;

@@ -29,7 +29,8 @@ struct PeerPtrsC { void* p[8]; };
 struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream);
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
+                            const PeerPtrsC* inbox, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
@@ -96,9 +97,11 @@ void StepExecutor::record_step(const void* x, const long long* y) {
   SignalPadsC sg;
   std::memcpy(g.p, cfg_.grad_ptrs, sizeof(g.p));
   std::memcpy(sg.pad, cfg_.sig_ptrs, sizeof(sg.pad));
+  PeerPtrsC ib;
+  std::memcpy(ib.p, cfg_.inbox_ptrs, sizeof(ib.p));
   int rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
                                     cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
-                                    cfg_.done_counter, cfg_.aux, compute_);
+                                    cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, compute_);
   if ((rc != 0 || rc2 != 0) && err_.empty())
     err_ = std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(rc ? rc : rc2));
 }

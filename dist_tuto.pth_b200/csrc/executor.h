@@ -28,6 +28,8 @@ struct StepConfig {
   long long sample_base, grad_stride;
   float lr, mu, p_drop;
   float* aux;                        // conv2.weight in the kernels' smem layouts (maintained by the SGD kernel)
+  void* inbox_ptrs[8];               // push exchange (sgd.cu): every rank's inbox
+  int push;
 };
 
 class StepExecutor {

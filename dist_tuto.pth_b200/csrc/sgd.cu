@@ -2,11 +2,13 @@
 //
 // Replaces average_gradients() + optimizer.step() + optimizer.zero_grad() of the reference training
 // step (train_dist.py:118,123,124): 8 all-reduces + 8 divides + foreach-SGD + 8 memsets become ONE
-// kernel.  Every rank reads all peers' gradient buckets over NVSwitch (one-shot), sums them in fixed
-// rank order (bit-identical replicas), scales, applies  buf = mu*buf + g ; p -= lr*buf  (torch.optim.SGD
-// semantics with dampening 0, no nesterov, no weight decay -- train_dist.py:110), then -- after a second
-// flag barrier that proves every peer has finished reading -- zeroes its own bucket for the next step's
-// `red.add` accumulation and bumps the device-side step counter used by the dropout RNG.
+// kernel, in two exchange flavours with identical arithmetic (fixed rank order => bit-identical replicas):
+//   * allreduce_sgd_push_kernel (default for world > 1): every rank stores its locally reduced bucket, flag-in-data,
+//     into every peer's inbox over NVSwitch and reduces out of its own memory -- one NVLink crossing on the critical path;
+//   * allreduce_sgd_kernel: flag barrier, then every rank loads all peers' buckets (one-shot).  Also the world == 1 path.
+// Both apply  buf = mu*buf + g ; p -= lr*buf  (torch.optim.SGD semantics with dampening 0, no nesterov, no weight
+// decay -- train_dist.py:110), re-zero the gradient bucket of the other step parity for the next `red.add` accumulation,
+// keep conv2.weight pre-arranged for the step kernels (`aux`) and bump the device step counter used by the dropout RNG.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,7 +31,29 @@ struct SgdArgs {
   int zero_grads;
   long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
   float* aux;                // optional [w2f 5000 | w2b 8000]: conv2.weight re-arranged for the forward/backward kernels
+  PeerPtrs inbox;            // push variant only: every rank's inbox  [2 parities][world sources][n_vec][2 lines of 16 B]
 };
+
+// SGD update of one float4 vector (+ the pre-arranged conv2.weight copies), shared by both exchange variants
+__device__ __forceinline__ void sgd_apply(const SgdArgs& a, size_t v, float4 g) {
+  g.x *= a.scale; g.y *= a.scale; g.z *= a.scale; g.w *= a.scale;
+  float4 m = reinterpret_cast<float4*>(a.momentum)[v];
+  float4 p = reinterpret_cast<float4*>(a.params)[v];
+  m.x = fmaf(a.mu, m.x, g.x); m.y = fmaf(a.mu, m.y, g.y); m.z = fmaf(a.mu, m.z, g.z); m.w = fmaf(a.mu, m.w, g.w);
+  p.x = fmaf(-a.lr, m.x, p.x); p.y = fmaf(-a.lr, m.y, p.y); p.z = fmaf(-a.lr, m.z, p.z); p.w = fmaf(-a.lr, m.w, p.w);
+  reinterpret_cast<float4*>(a.momentum)[v] = m;
+  reinterpret_cast<float4*>(a.params)[v] = p;
+  if (a.aux != nullptr && v >= 264 / 4 && v < (264 + 5000) / 4) {      // conv2.weight (flat offset 264, 5000 elements)
+    const float pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = (int)v * 4 + e - 264;
+      const int co = i / 250, r = i - co * 250, ci = r / 25, kk = r - ci * 25;
+      a.aux[(ci * 25 + kk) * 20 + co] = pw[e];                                     // w2f [ci][ky][kx][co]
+      a.aux[5000 + ((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = pw[e];            // w2b [co][ky][kx][half][8]
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   const int rank = a.rank, world = a.world;
@@ -75,23 +99,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
           g.x += __uint_as_float(raw[r].x); g.y += __uint_as_float(raw[r].y);
           g.z += __uint_as_float(raw[r].z); g.w += __uint_as_float(raw[r].w);
         }
-      g.x *= a.scale; g.y *= a.scale; g.z *= a.scale; g.w *= a.scale;
-      float4 m = reinterpret_cast<float4*>(a.momentum)[v];
-      float4 p = reinterpret_cast<float4*>(a.params)[v];
-      m.x = fmaf(a.mu, m.x, g.x); m.y = fmaf(a.mu, m.y, g.y); m.z = fmaf(a.mu, m.z, g.z); m.w = fmaf(a.mu, m.w, g.w);
-      p.x = fmaf(-a.lr, m.x, p.x); p.y = fmaf(-a.lr, m.y, p.y); p.z = fmaf(-a.lr, m.z, p.z); p.w = fmaf(-a.lr, m.w, p.w);
-      reinterpret_cast<float4*>(a.momentum)[v] = m;
-      reinterpret_cast<float4*>(a.params)[v] = p;
-      if (a.aux != nullptr && v >= 264 / 4 && v < (264 + 5000) / 4) {      // conv2.weight (flat offset 264, 5000 elements)
-        const float pw[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = (int)v * 4 + e - 264;
-          const int co = i / 250, r = i - co * 250, ci = r / 25, kk = r - ci * 25;
-          a.aux[(ci * 25 + kk) * 20 + co] = pw[e];                                     // w2f [ci][ky][kx][co]
-          a.aux[5000 + ((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = pw[e];            // w2b [co][ky][kx][half][8]
-        }
-      }
+      sgd_apply(a, v, g);
     }
     if (a.zero_grads) {
       if (dbuf) {
@@ -105,6 +113,81 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   if (world > 1 && threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
   // the last block to have checked in knows every block has read the step counter: it publishes step + 1
   if (threadIdx.x == 0 && a.step != nullptr && seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
+}
+
+// Push ("LL") variant of the same step: no flag barrier and no remote loads.
+//
+// Every rank STORES its locally reduced bucket into every peer's inbox as 16-byte lines {v0, epoch, v1, epoch}
+// (the flag travels with the data, so one NVLink crossing both delivers and publishes it), then sums the world lines of
+// each element out of its OWN memory, polling until both flags of a line carry this step's epoch.  Compared with
+// barrier + peer loads (flag crossing, then a load round trip) the critical path is ONE one-way crossing.  The sum
+// runs in fixed rank order with the own contribution taken from registers at position `rank`, so replicas stay
+// bit-identical and equal to the barrier variant.  epoch = step + 1 (never 0 = freshly zeroed inbox); lines are
+// double-buffered by step parity: a peer can only write parity p again two steps later, which needs my push of the
+// step in between, which I issue after I finished reading parity p.
+__global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs a) {
+  const int rank = a.rank, world = a.world;
+  __shared__ unsigned long long s_step;
+  pdl_wait();
+  pdl_launch_dependents();
+  unsigned int seen = 0u;
+  if (threadIdx.x == 0) {
+    s_step = *reinterpret_cast<volatile unsigned long long*>(a.step);
+    seen = atomicAdd(a.done_counter, 1u);
+  }
+  __syncthreads();
+  const unsigned long long st = s_step;
+  const uint32_t epoch = (uint32_t)(st + 1ull);
+  const size_t par = (size_t)(st & 1ull);
+  const size_t cur_off = par * (size_t)a.grad_stride * sizeof(float);
+  const size_t oth_off = (par ^ 1) * (size_t)a.grad_stride * sizeof(float);
+  const size_t stride = (size_t)gridDim.x * kSgdThreads;
+  for (size_t v = (size_t)blockIdx.x * kSgdThreads + threadIdx.x; v < a.n_vec; v += stride) {
+    const uint4 mine = ld_cg_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.grads.p[rank]) + cur_off) + v);
+    // line index inside an inbox: ((parity * world + source) * n_vec + v) * 2
+    const size_t dst_line = ((par * (size_t)world + (size_t)rank) * a.n_vec + v) * 2;
+    const uint4 l0 = make_uint4(mine.x, epoch, mine.y, epoch), l1 = make_uint4(mine.z, epoch, mine.w, epoch);
+#pragma unroll
+    for (int i = 1; i < B2_MAX_RANKS; ++i) {          // start with the next rank so the ranks do not all hit one peer first
+      if (i < world) {
+        int r = rank + i;
+        if (r >= world) r -= world;
+        uint4* dst = reinterpret_cast<uint4*>(a.inbox.p[r]) + dst_line;
+        st_volatile_v4(dst, l0);
+        st_volatile_v4(dst + 1, l1);
+      }
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint4* in = reinterpret_cast<const uint4*>(a.inbox.p[rank]);
+#pragma unroll
+    for (int r = 0; r < B2_MAX_RANKS; ++r) {
+      if (r < world) {
+        uint4 q0, q1;
+        if (r == rank) {
+          q0 = l0; q1 = l1;
+        } else {
+          const uint4* src = in + ((par * (size_t)world + (size_t)r) * a.n_vec + v) * 2;
+          unsigned long long spins = 0;
+          for (;;) {
+            q0 = ld_volatile_v4(src);
+            q1 = ld_volatile_v4(src + 1);
+            if (q0.y == epoch && q0.w == epoch && q1.y == epoch && q1.w == epoch) break;
+            if (++spins > B2_SPIN_LIMIT) {
+              printf("[b200dist] push all-reduce: rank %d timed out waiting for rank %d (step %llu, vector %llu)\n", rank, r, st,
+                     (unsigned long long)v);
+              __trap();
+            }
+          }
+        }
+        g.x += __uint_as_float(q0.x); g.y += __uint_as_float(q0.z);
+        g.z += __uint_as_float(q1.x); g.w += __uint_as_float(q1.z);
+      }
+    }
+    sgd_apply(a, v, g);
+    if (a.zero_grads)
+      st_cg_v4(reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.grads.p[rank]) + oth_off) + v, make_uint4(0u, 0u, 0u, 0u));
+  }
+  if (threadIdx.x == 0 && seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
 }
 
 // Plain flat momentum SGD (generic models: gradients already averaged in `grad`)
@@ -140,8 +223,16 @@ extern "C" {
 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
-                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux, cudaStream_t stream) {
+                            int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
+                            const PeerPtrs* inbox, cudaStream_t stream) {
   b2::SgdArgs a;
+  memset(&a.inbox, 0, sizeof(a.inbox));
+  // push ("LL") exchange: needs an inbox on every rank, the double-buffered buckets and the device step counter (its epoch)
+  const bool push = inbox != nullptr && world > 1;
+  if (push) {
+    if (step == nullptr || grad_stride <= 0) return (int)cudaErrorInvalidValue;
+    a.inbox = *inbox;
+  }
   a.grads = *grads; a.sig = *sig; a.params = params; a.momentum = momentum; a.step = step;
   a.n_vec = n_elems / 4; a.lr = lr; a.mu = mu; a.scale = scale; a.rank = rank; a.world = world;
   a.zero_grads = zero_grads; a.grad_stride = grad_stride; a.done_counter = done_counter; a.aux = aux;
@@ -160,7 +251,8 @@ int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, fl
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_kernel, a);
+  return push ? (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_push_kernel, a)
+              : (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_kernel, a);
 }
 
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,

@@ -149,6 +149,13 @@ class FusedTrainer:
         else:
             self.grads = torch.zeros(2 * NPAR_ALLOC, dtype=torch.float32, device=self.device)
             self._grad_ptrs, self._sig_ptrs = [self.grads.data_ptr()], [0]
+        # push exchange (csrc/sgd.cu, allreduce_sgd_push_kernel): every rank stores its bucket, flag-in-data, into every
+        # peer's inbox and then reduces out of local memory -- one NVLink crossing instead of flag barrier + load round trip
+        self.inbox_handle, self._inbox_ptrs = None, []
+        if self.world > 1 and os.environ.get("B200DIST_SGD_PUSH", "1") != "0":
+            self.inbox_handle = self.symm.alloc(2 * self.world * (NPAR_ALLOC // 4) * 8, torch.int32)
+            self._inbox_ptrs = self.inbox_handle.ptrs
+            self._reset_exchange()
         # two gradient buckets, selected by (step & 1) inside the kernels: the all-reduce kernel re-zeroes the bucket
         # of the previous step, which needs no second cross-GPU barrier (see csrc/sgd.cu)
         self.grad_stride = NPAR_ALLOC
@@ -177,6 +184,22 @@ class FusedTrainer:
         self.gpu_launches_per_step = 2              # convnet_step + allreduce_sgd (our kernels)
         self._warm()
 
+    def _reset_exchange(self):
+        """Collective: bring the cross-step exchange state back to 'before the first step' -- both gradient buckets zero
+        (the kernels only re-zero the bucket of the previous parity) and the push inbox empty (epoch 0).  Called at
+        construction and whenever the step counter, which selects the bucket and is the epoch source, is rewritten.
+        The barriers make sure no peer is still reading our bucket / writing our inbox, and that nobody starts stepping
+        before everyone has cleaned up."""
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            comm.barrier(self.group)
+        self.grads.zero_()
+        if self.inbox_handle is not None:
+            self.inbox_handle.local.zero_()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            comm.barrier(self.group)
+
     def _refresh_aux(self):
         """(Re)build the pre-arranged conv2.weight copies from the flat parameters (init / load_state_dict)."""
         w2 = self.params[LAYOUT["conv2.weight"]:LAYOUT["conv2.weight"] + 5000].view(20, 10, 25)
@@ -192,7 +215,7 @@ class FusedTrainer:
                             self.cluster if B * self.cluster <= 148 else 1, self.aux)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
-                             self.done_counter, self.aux)
+                             self.done_counter, self.aux, self._inbox_ptrs)
 
     def _warm(self):
         # forward-only launch: sets the kernel's dynamic-smem attribute outside of graph capture
@@ -312,7 +335,7 @@ class FusedTrainer:
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
-                                      self.cluster, self.aux, chunk),
+                                      self.cluster, self.aux, chunk, self._inbox_ptrs),
                   self.training)
             self._executors[id(loader)] = ex
         if new_epoch:
@@ -385,6 +408,7 @@ class FusedTrainer:
                 mv[k].copy_(v)
         if "steps" in sd:
             self.step_counter.fill_(int(sd["steps"]))
+            self._reset_exchange()               # bucket parity and push epochs derive from the step counter
         self._refresh_aux()
         torch.cuda.synchronize(self.device)
 

@@ -157,6 +157,48 @@ def w_fused_trainer(rank, size):
     dist.barrier()
 
 
+def w_push_exchange_equals_barrier_exchange(rank, size):
+    """allreduce_sgd_push_kernel (flag-in-data stores into the peers' inboxes) == barrier + peer loads,
+    through the Python graph path, the C++ executor and a load_state_dict() rewind of the step counter (epoch reuse)."""
+    import os
+    dev = _dev()
+    from dist_tuto.pth_b200 import data as D
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    bsz = 16
+    ds = D.SyntheticMNIST(n=bsz * size * 12 + 5 * size, seed=4)        # 12 full batches + a short tail per rank
+    idx = list(range(rank, len(ds), size))
+    results = {}
+    for push in ("0", "1"):
+        os.environ["B200DIST_SGD_PUSH"] = push
+        tr = FusedTrainer(bsz, lr=0.05, seed=11, device=dev, p_drop=0.5, raw_uint8=True)
+        assert (tr.inbox_handle is not None) == (push == "1")
+        for i in range(7):                                             # python graph path, odd count -> both parities
+            g = torch.Generator().manual_seed(50 + i * size + rank)
+            tr.step(torch.randint(0, 255, (bsz, 1, 28, 28), generator=g, dtype=torch.uint8).pin_memory(),
+                    torch.randint(0, 10, (bsz,), generator=g).pin_memory())
+        tr.sync_lag(0)
+        snap = tr.state_dict()
+        loader = D.NativeBatchLoader(D.Partition(ds, idx), bsz, seed=3, raw_uint8=True, pin_memory=True)
+        done, fin = tr.run_native(loader)                              # C++ executor + eager short tail
+        assert done == 13 and fin
+        tr.load_state_dict(snap)                                       # rewinds the step counter: inbox epochs are reused
+        done, _ = tr.run_native(loader, max_steps=9)
+        assert done == 9
+        torch.cuda.synchronize()
+        results[push] = (tr.params.clone(), tr.momentum.clone(), int(tr.step_counter.item()))
+        del tr
+    os.environ.pop("B200DIST_SGD_PUSH", None)
+    assert results["0"][2] == results["1"][2] == 16
+    # same maths in the same rank order; run-to-run differences only from the float-atomic gradient flush inside a GPU
+    assert torch.allclose(results["0"][0], results["1"][0], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(results["0"][1], results["1"][1], atol=2e-5, rtol=1e-4)
+    mine = results["1"][0].clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other)
+    dist.barrier()
+
+
 def w_p2p_ring_gpu(rank, size):
     dev = _dev()
     t = torch.zeros(4, device=dev)

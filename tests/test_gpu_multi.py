@@ -29,6 +29,10 @@ def test_fused_trainer_equals_global_batch_sgd():
     go(W.w_fused_trainer)
 
 
+def test_push_exchange_equals_barrier_exchange():
+    go(W.w_push_exchange_equals_barrier_exchange)
+
+
 def test_nccl_p2p_and_ring_allreduce():
     go(W.w_p2p_ring_gpu)
 
