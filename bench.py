@@ -132,6 +132,8 @@ def ours(args):
                               extra_config={"engine": "fused convnet_step (cluster-per-sample for small per-GPU batches) + allreduce_sgd kernels, CUDA graph, PDL",
                                             "precision": "fp32 SIMT forward/backward (>= the required bf16); fp32 gradients on the wire; fp32 SGD",
                                             "cluster_ctas_per_sample": tr.cluster,
+                                            "gradient_exchange": ("push: flag-in-data stores into peer inboxes, local reduce" if tr.inbox_handle is not None
+                                                                  else ("barrier + peer loads" if size > 1 else "none (1 GPU)")),
                                             "l2": f"inputs cycle through a {pool * batch_bytes >> 20} MB device pool (> 126 MB L2)",
                                             "graph_chunk": G, "symm": sym,
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
