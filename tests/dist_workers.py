@@ -164,6 +164,37 @@ def w_average_gradients(rank, size):
     b2.barrier()
 
 
+def w_flat_sgd_ddp(rank, size):
+    """Tutorial loop with DistributedDataParallel + FlatSGD on N ranks == torch.optim.SGD on the global batch."""
+    import torch.nn.functional as F
+    torch.manual_seed(7)
+    ref = b2.Net().eval()
+    mine = b2.Net().eval()
+    mine.load_state_dict({k: v.clone() for k, v in ref.state_dict().items()})
+    ddp = DistributedDataParallel(mine, bucket_cap_bytes=16384)
+    opt = b2.FlatSGD(ddp, lr=0.05, momentum=0.5)
+    assert len(opt.buckets) > 1
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.5)
+    for it in range(3):
+        g = torch.Generator().manual_seed(200 + it)
+        x, y = torch.randn(8 * size, 1, 28, 28, generator=g), torch.randint(0, 10, (8 * size,), generator=g)
+        opt.zero_grad()
+        F.nll_loss(ddp(x[rank * 8:(rank + 1) * 8]), y[rank * 8:(rank + 1) * 8]).backward()
+        b2.average_gradients(mine)
+        opt.step()
+        ref_opt.zero_grad()
+        F.nll_loss(ref(x), y).backward()                   # mean over the global batch == mean of the per-rank means
+        ref_opt.step()
+    for (n, a), b in zip(ref.named_parameters(), mine.parameters()):
+        assert torch.allclose(a, b, atol=1e-5), n
+    for b in opt.buckets:                                  # step() left the buckets zeroed
+        assert float(b.flat.abs().max()) == 0.0
+    flat = torch.cat([p.detach().reshape(-1) for p in mine.parameters()])
+    other = flat.clone()
+    b2.broadcast(other, src=0)
+    assert torch.equal(flat, other)                        # replicas identical
+
+
 def w_train(rank, size):
     ds = SyntheticMNIST(n=1024, seed=5)
     logs = []

@@ -33,6 +33,10 @@ def test_average_gradients_and_ddp_world2():
     go(W.w_average_gradients, 2)
 
 
+def test_flat_sgd_with_ddp_world2_equals_global_batch_sgd():
+    go(W.w_flat_sgd_ddp, 2)
+
+
 def test_train_loop_world2_replicas_identical():
     go(W.w_train, 2)
 
