@@ -29,6 +29,7 @@ from . import comm
 from .data import partition_dataset
 from .models.convnet import Net
 from .ops.optim import FlatSGD
+from .utils import say
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
 __all__ = ["run", "train", "TrainConfig"]
@@ -39,7 +40,7 @@ class TrainConfig:
 
     def __init__(self, epochs: int = 10, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234,
                  global_batch: int = 128, engine: str = "auto", device: Optional[str] = None,
-                 max_steps: Optional[int] = None, dataset=None, log: Callable[..., None] = print,
+                 max_steps: Optional[int] = None, dataset=None, log: Callable[..., None] = say,
                  p_drop: float = 0.5, checkpoint: Optional[str] = None, resume: Optional[str] = None):
         self.epochs, self.lr, self.momentum, self.seed = epochs, lr, momentum, seed
         self.global_batch, self.engine, self.device = global_batch, engine, device

@@ -16,6 +16,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dist_tuto.pth_b200 as dist  # noqa: E402
+from dist_tuto.pth_b200.utils import say  # noqa: E402  (print as one write: ranks share the terminal)
 
 
 def run(rank, size):
@@ -33,7 +34,7 @@ def run(rank, size):
         r = out
     if cuda:
         torch.cuda.synchronize()
-    print("Rank ", rank, "\n collective:", t.flatten().tolist(), "\n ring:      ", r.flatten().tolist())
+    say("Rank ", rank, "\n collective:", t.flatten().tolist(), "\n ring:      ", r.flatten().tolist())
     assert torch.allclose(t, r, rtol=1e-4)
 
 

@@ -13,16 +13,17 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dist_tuto.pth_b200 as dist  # noqa: E402
+from dist_tuto.pth_b200.utils import say  # noqa: E402  (print as one write: ranks share the terminal)
 
 
 def run(rank, size):
-    print(dist.get_world_size())
+    say(dist.get_world_size())
     cuda = torch.cuda.is_available() and "nccl" in str(torch.distributed.get_backend())
     dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     tensor = torch.ones(1, device=dev)
     tensor_list = [torch.zeros(1, device=dev) for _ in range(size)]
     dist.gather(tensor, dst=0, gather_list=tensor_list, group=0)     # group=0 == world, as in 2017
-    print("Rank ", rank, " has data ", sum(tensor_list)[0].item())
+    say("Rank ", rank, " has data ", sum(tensor_list)[0].item())
 
 
 if __name__ == "__main__":

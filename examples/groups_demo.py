@@ -7,6 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dist_tuto.pth_b200 as dist  # noqa: E402
+from dist_tuto.pth_b200.utils import say  # noqa: E402  (print as one write: ranks share the terminal)
 
 
 def run(rank, size):
@@ -14,7 +15,7 @@ def run(rank, size):
     tensor = torch.ones(1)
     if rank in (0, 1):
         dist.all_reduce(tensor, op=dist.reduce_op.SUM, group=group)
-    print("Rank ", rank, " has data ", tensor[0].item())
+    say("Rank ", rank, " has data ", tensor[0].item())
 
 
 if __name__ == "__main__":

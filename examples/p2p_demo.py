@@ -14,6 +14,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dist_tuto.pth_b200 as dist  # noqa: E402
+from dist_tuto.pth_b200.utils import say  # noqa: E402  (print as one write: ranks share the terminal)
 
 CUDA = False
 
@@ -26,18 +27,18 @@ def run(rank, size):
         dist.send(tensor=tensor, dst=1)           # blocks until the buffer may be reused
     else:
         dist.recv(tensor=tensor, src=0)           # receiver pre-allocates
-    print("[blocking]     Rank ", rank, " has data ", tensor[0].item())
+    say("[blocking]     Rank ", rank, " has data ", tensor[0].item())
 
     tensor = torch.zeros(1, device=dev)
     if rank == 0:
         tensor += 1
         req = dist.isend(tensor=tensor, dst=1)
-        print("Rank 0 started sending")
+        say("Rank 0 started sending")
     else:
         req = dist.irecv(tensor=tensor, src=0)
-        print("Rank 1 started receiving")
+        say("Rank 1 started receiving")
     req.wait(sync=True)                           # do not touch `tensor` before this returns
-    print("[non-blocking] Rank ", rank, " has data ", tensor[0].item())
+    say("[non-blocking] Rank ", rank, " has data ", tensor[0].item())
 
 
 if __name__ == "__main__":

@@ -13,10 +13,11 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dist_tuto.pth_b200 as dist  # noqa: E402
 
-CFG = {}
+import json  # noqa: E402
 
 
 def run(rank, size):
+    CFG = json.loads(os.environ["B2_TRAIN_CFG"])          # spawned ranks re-import this file: pass the CLI through the env
     cfg = dist.TrainConfig(epochs=CFG["epochs"], lr=CFG["lr"], max_steps=CFG["max_steps"], checkpoint=CFG["ckpt"])
     out = dist.train(rank, size, cfg)
     if rank == 0:
@@ -33,7 +34,7 @@ if __name__ == "__main__":
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--external", action="store_true", help="rank/size from torchrun/mpirun env")
     a = ap.parse_args()
-    CFG.update(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint)
+    os.environ["B2_TRAIN_CFG"] = json.dumps(dict(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint))
     if a.external:
         dist.init_from_env(run, backend=a.backend)
     else:
