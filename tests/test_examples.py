@@ -47,3 +47,28 @@ def test_train_mnist_example_two_ranks_few_steps():
     lines = re.findall(r"Rank\s+(\d)\s*, epoch\s+0\s*:\s+([0-9.]+)", out)     # train_dist.py:125-127 print format
     assert sorted(r for r, _ in lines) == ["0", "1"]
     assert all(0.5 < float(v) < 5.0 for _, v in lines)
+
+
+def torchrun(nproc, script, *args):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "examples", script), *args],
+                       capture_output=True, text=True, timeout=280, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def test_external_launcher_env_recipe_train():
+    """rank/size from an external launcher (the tutorial's MPI recipe, tuto.md:383-398; here torchrun provides the env)."""
+    out = torchrun(2, "train_mnist.py", "--external", "--backend", "gloo", "--epochs", "1", "--max-steps", "4")
+    assert sorted(re.findall(r"Rank\s+(\d)\s*, epoch\s+0", out)) == ["0", "1"]
+
+
+def test_mpi_backend_recipe_allreduce_demo():
+    out = torchrun(3, "allreduce_demo.py", "--backend", "mpi")          # init_processes(0, 0, run, backend='mpi')
+    rings = re.findall(r"ring:\s+(\[.*?\])", out)
+    assert len(rings) == 3 and len(set(rings)) == 1
