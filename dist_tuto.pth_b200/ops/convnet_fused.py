@@ -4,12 +4,14 @@ One training step of the reference (train_dist.py:118-124:
 ``zero_grad -> model(data) -> nll_loss -> backward -> average_gradients -> step``)
 is TWO kernels here, replayed as one CUDA graph:
 
-  1. ``convnet_step``   (csrc/convnet.cu)  forward + loss + backward, one CTA per
-     sample, gradients ``red.add``-ed into a flat fp32 bucket that lives in
-     symmetric peer memory;
-  2. ``allreduce_sgd``  (csrc/sgd.cu)      every rank reads all peers' buckets over
-     NVSwitch, averages, applies momentum SGD to the flat fp32 parameters,
-     re-zeroes its bucket and bumps the RNG step counter.
+  1. ``convnet_step``   (csrc/convnet.cu, csrc/convnet_cluster.cu)  forward + loss +
+     backward, one CTA (or one 2/4/8-CTA cluster) per sample, gradients
+     ``red.add``-ed into a flat fp32 bucket that lives in symmetric peer memory;
+  2. ``allreduce_sgd``  (csrc/sgd.cu)      every rank stores its bucket, flag-in-data,
+     into every peer's inbox over NVSwitch (or, ``B200DIST_SGD_PUSH=0``: flag barrier
+     + loads of the peers' buckets), averages in fixed rank order, applies momentum
+     SGD to the flat fp32 parameters, re-zeroes the bucket of the other step parity
+     and bumps the RNG step counter.
 
 The graph also contains the H2D copy of the batch from a pinned staging slot
 and the D2H copy of the running loss, so the host issues ONE launch per step.
