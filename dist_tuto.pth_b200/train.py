@@ -30,6 +30,7 @@ from .data import partition_dataset
 from .models.convnet import Net
 from .ops.optim import FlatSGD
 from .utils import say
+from .utils.checkpoint import load_checkpoint, save_checkpoint
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
 __all__ = ["run", "train", "TrainConfig"]
@@ -69,21 +70,25 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     train_set, bsz = partition_dataset(cfg.dataset, global_batch=cfg.global_batch, seed=cfg.seed,
                                        **({"raw_uint8": True} if fused_raw else {}))
     num_batches = ceil(len(train_set.dataset) / float(bsz))      # train_dist.py:112
+    start_steps, optimizer, resume_blob = 0, None, {}
     if engine == "fused":
         from .ops.convnet_fused import FusedTrainer
         trainer = FusedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
                                p_drop=cfg.p_drop, raw_uint8=fused_raw)
         if cfg.resume:
-            trainer.load_state_dict(torch.load(cfg.resume, map_location="cpu"))
+            start_steps = int(load_checkpoint(cfg.resume, trainer).get("steps", 0))
         step_fn, epoch_loss_fn, model = trainer.step, trainer.pop_loss_sum, trainer
     else:
         model = Net(cfg.p_drop).to(device)
         if cfg.resume:
-            model.load_state_dict(torch.load(cfg.resume, map_location="cpu")["model"])
+            resume_blob = load_checkpoint(cfg.resume, model)
+            start_steps = int(resume_blob.get("steps", 0))
         broadcast_parameters(model)
         model._grad_bucket = GradBucket(list(model.parameters()))
         # optim.SGD(lr=0.01, momentum=0.5) of train_dist.py:110, over flat buffers: update + zero_grad in one pass
         optimizer = FlatSGD(model, lr=cfg.lr, momentum=cfg.momentum)
+        if cfg.resume and "optim" in resume_blob:
+            optimizer.load_state_dict(resume_blob["optim"])          # momentum buffers
         acc = torch.zeros((), device=device)
 
         def step_fn(data, target):
@@ -129,8 +134,7 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
             break
     elapsed = time.perf_counter() - t0
     if cfg.checkpoint and comm.get_rank() == 0:
-        from .utils.checkpoint import save_checkpoint
-        save_checkpoint(cfg.checkpoint, model, steps=steps, history=history)
+        save_checkpoint(cfg.checkpoint, model, optimizer=optimizer, steps=start_steps + steps, history=history)
     return {"loss": history, "steps": steps, "seconds": elapsed, "bsz": bsz,
             "samples_per_s": steps * bsz * size / max(elapsed, 1e-9), "model": model}
 

@@ -31,13 +31,14 @@ def save_checkpoint(path: str, model, optimizer=None, **extra: Any) -> str:
 
 
 def load_checkpoint(path: str, model=None, optimizer=None, map_location="cpu") -> Dict[str, Any]:
+    """Restore ``model`` (an ``nn.Module`` or a fused trainer) and, when given, ``optimizer`` (``torch.optim`` or
+    ``FlatSGD``) from ``path``; returns the whole blob (``steps``, ``history``, ...)."""
     blob = torch.load(path, map_location=map_location)
     if model is not None:
-        if hasattr(model, "load_state_dict"):
-            try:
-                model.load_state_dict(blob["model"])
-            except Exception:
-                model.load_state_dict(blob)
+        if isinstance(model, torch.nn.Module):
+            model.load_state_dict(blob["model"])
+        else:                                   # fused trainer: parameters + momentum + step counter in one dict
+            model.load_state_dict(blob)
     if optimizer is not None and "optim" in blob:
         optimizer.load_state_dict(blob["optim"])
     return blob

@@ -407,3 +407,30 @@ def test_load_state_dict_rewinds_step_parity_and_buckets(dev):
     assert int(tr.step_counter.item()) == int(fresh.step_counter.item()) == 11
     # (not bit-equal: the per-CTA gradient flush is a float atomic, its order varies run to run)
     assert torch.allclose(again, fresh.params, atol=2e-5, rtol=1e-4)
+
+
+def test_fused_trainer_checkpoint_roundtrip_restores_momentum_and_steps(dev, tmp_path):
+    """save_checkpoint / load_checkpoint on the fused trainer: parameters, momentum AND the device step counter."""
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    from dist_tuto.pth_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+
+    def batch(i):
+        g = torch.Generator().manual_seed(2000 + i)
+        return torch.randn(32, 1, 28, 28, generator=g).pin_memory(), torch.randint(0, 10, (32,), generator=g).pin_memory()
+
+    a = FusedTrainer(32, lr=0.05, momentum=0.9, seed=1, device=dev, p_drop=0.0)
+    for i in range(5):
+        a.step(*batch(i))
+    path = save_checkpoint(str(tmp_path / "t.pt"), a, history=[0.5])
+    for i in range(5, 8):
+        a.step(*batch(i))
+    a.sync_lag(0)
+    b = FusedTrainer(32, lr=0.05, momentum=0.9, seed=99, device=dev, p_drop=0.0)      # different init
+    blob = load_checkpoint(path, b)
+    assert blob["steps"] == 5 and int(b.step_counter.item()) == 5 and float(b.momentum.abs().sum()) > 0
+    for i in range(5, 8):
+        b.step(*batch(i))
+    b.sync_lag(0)
+    torch.cuda.synchronize()
+    assert torch.allclose(a.params, b.params, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(a.momentum, b.momentum, atol=2e-5, rtol=1e-4)
