@@ -24,7 +24,6 @@ import importlib.util
 import json
 import os
 import sys
-import tempfile
 import time
 import warnings
 

@@ -28,7 +28,7 @@ import sys
 import time
 import traceback
 import warnings
-from typing import Callable, Optional, Sequence
+from typing import Callable, Optional
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,7 @@ arrays once.  (The ConvNet goes further and fuses the all-reduce into the same k
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn

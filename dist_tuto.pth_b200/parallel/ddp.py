@@ -20,7 +20,7 @@ B200-first design instead of "one blocking all_reduce + one divide per tensor":
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -7,7 +7,7 @@ using the reference's parameter names, so checkpoints interchange)."""
 from __future__ import annotations
 
 import os
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 import torch
 

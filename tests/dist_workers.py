@@ -3,7 +3,7 @@ import torch
 import torch.nn.functional as F
 
 import dist_tuto.pth_b200 as b2
-from dist_tuto.pth_b200 import comm, ring
+from dist_tuto.pth_b200 import ring
 from dist_tuto.pth_b200.data import SyntheticMNIST
 from dist_tuto.pth_b200.parallel.ddp import DistributedDataParallel, GradBucket
 

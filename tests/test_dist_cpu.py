@@ -1,5 +1,4 @@
 """Distributed-CPU tier: N local processes on gloo @127.0.0.1."""
-import os
 
 import pytest
 
