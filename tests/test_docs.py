@@ -29,3 +29,15 @@ def test_tutorial_renders_with_figures():
     for sec in ("Setup", "Point-to-Point Communication", "Collective Communication", "Distributed Training",
                 "Our Own Ring-Allreduce", "Communication Backends", "Initialization Methods"):
         assert sec in html          # the section structure of tuto.md
+
+
+def test_api_reference_lists_every_tutorial_name(tmp_path, monkeypatch):
+    import build_api
+    monkeypatch.setattr(build_api, "HERE", str(tmp_path))
+    build_api.main()
+    text = open(tmp_path / "api.md").read()
+    # the API surface the tutorial documents
+    for name in ("init_processes", "send", "recv", "isend", "irecv", "new_group", "all_reduce", "reduce", "broadcast", "scatter",
+                 "gather", "all_gather", "reduce_op", "allreduce", "Partition", "DataPartitioner", "partition_dataset", "Net",
+                 "average_gradients", "run"):
+        assert f"`{name}" in text, name
