@@ -1,0 +1,46 @@
+"""Script launcher (dist_tuto.pth_b200.spawn): env rendezvous, failure propagation, timeout -- the supervised
+counterpart of the reference's `__main__` fork/join block (train_dist.py:138-147)."""
+import os
+import subprocess
+import sys
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = os.path.join(ROOT, "tests", "spawn_scripts.py")
+pytestmark = pytest.mark.timeout(240)
+
+
+def launch(*args):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+    t0 = time.monotonic()
+    p = subprocess.run([sys.executable, "-m", "dist_tuto.pth_b200.spawn", *args], capture_output=True, text=True, env=env,
+                       cwd=ROOT, timeout=200)
+    return p, time.monotonic() - t0
+
+
+def test_ranks_rendezvous_through_the_env():
+    p, _ = launch("--size", "3", SCRIPT, "allreduce")
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = sorted(l for l in p.stdout.splitlines() if l.startswith("rank"))
+    assert lines == [f"rank {r} of 3 sum 6.0" for r in range(3)]
+
+
+def test_first_failure_stops_the_job_with_that_exit_code():
+    p, dt = launch("--size", "3", SCRIPT, "fail")
+    assert p.returncode == 7 and "rank 1 exited with code 7" in p.stderr
+    assert dt < 60                                       # the sleeping survivors were terminated, not joined
+
+
+def test_timeout_kills_every_rank():
+    p, dt = launch("--size", "2", "--timeout", "2", SCRIPT, "hang")
+    assert p.returncode == 124 and "exceeded" in p.stderr and dt < 60
+
+
+def test_run_script_api_returns_zero(tmp_path):
+    from dist_tuto.pth_b200.spawn import run_script
+    ok = tmp_path / "ok.py"
+    ok.write_text("import os, sys\nassert int(os.environ['WORLD_SIZE']) == 2 and os.environ['MASTER_ADDR'] == '127.0.0.1'\n"
+                  "assert os.environ['RANK'] == os.environ['LOCAL_RANK']\n")
+    assert run_script(str(ok), size=2, timeout_s=60) == 0
