@@ -1,6 +1,6 @@
 """Debug: native executor vs python loop vs eager loop, checksums after each epoch phase."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dist_tuto.pth_b200 import data as D
 from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
 dev = torch.device("cuda:0")
