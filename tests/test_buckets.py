@@ -1,0 +1,68 @@
+"""Property tests for the flat gradient-bucket layout ("random sizes/offsets ... bucket layout")."""
+import torch
+import torch.nn as nn
+from hypothesis import given, settings, strategies as st
+
+from dist_tuto.pth_b200.parallel.ddp import DistributedDataParallel, GradBucket
+
+shapes = st.lists(st.lists(st.integers(1, 7), min_size=1, max_size=4), min_size=1, max_size=8)
+
+
+def _params(shape_list, channels_last=False):
+    ps = []
+    for s in shape_list:
+        t = torch.randn(*s)
+        if channels_last and len(s) == 4:
+            t = t.contiguous(memory_format=torch.channels_last)
+        ps.append(nn.Parameter(t))
+    return ps
+
+
+@settings(max_examples=60, deadline=None)
+@given(shape_list=shapes, align=st.sampled_from([1, 4, 16]), cl=st.booleans())
+def test_views_tile_the_flat_buffer_without_overlap(shape_list, align, cl):
+    ps = _params(shape_list, cl)
+    gb = GradBucket(ps, align=align, symmetric=False)
+    assert gb.numel >= sum(p.numel() for p in ps) and gb.flat.numel() == gb.numel
+    # offsets: aligned, increasing, segment i ends before segment i+1 starts
+    for i, (o, p) in enumerate(zip(gb.offsets, ps)):
+        assert o % align == 0
+        if i + 1 < len(ps):
+            assert o + p.numel() <= gb.offsets[i + 1]
+    # every view aliases exactly its own segment and has the parameter's shape and strides
+    gb.flat.zero_()
+    for i, (v, p, o) in enumerate(zip(gb.views, ps, gb.offsets)):
+        assert v.shape == p.shape and v.stride() == p.stride() and p.grad is v
+        v.fill_(float(i + 1))
+        seg = gb.flat[o:o + p.numel()]
+        assert bool((seg == float(i + 1)).all())
+    # nothing was written outside the segments (alignment padding stays zero)
+    written = sum(p.numel() * (i + 1) for i, p in enumerate(ps))
+    assert float(gb.flat.sum()) == float(written)
+
+
+@settings(max_examples=40, deadline=None)
+@given(shape_list=shapes, cap=st.integers(4, 4096))
+def test_ddp_buckets_partition_the_parameters_in_reverse_order(shape_list, cap):
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = nn.ParameterList(_params(shape_list))
+
+        def forward(self, x):
+            return sum((p * x).sum() for p in self.ps)
+
+    m = M()
+    ddp = DistributedDataParallel(m, bucket_cap_bytes=cap, broadcast=False)
+    flat_order = [p for b in ddp.buckets for p in b.params]
+    assert [id(p) for p in flat_order] == [id(p) for p in reversed(list(m.parameters()))]      # backward order
+    for b in ddp.buckets:                       # a bucket only exceeds the cap when a single parameter does
+        nbytes = sum(p.numel() * 4 for p in b.params)
+        assert nbytes <= cap or len(b.params) == 1
+    # one backward fills every bucket through the views; averaging at world 1 is the identity
+    ddp.zero_grad()
+    ddp(torch.tensor(2.0)).backward()
+    ddp.finish()
+    for p in m.parameters():
+        assert torch.allclose(p.grad, torch.full_like(p, 2.0))
+    ddp.remove_hooks()
