@@ -195,6 +195,44 @@ def w_flat_sgd_ddp(rank, size):
     assert torch.equal(flat, other)                        # replicas identical
 
 
+def w_symm_fd_exchange(rank, size):
+    """Host side of the symmetric-memory runtime without a GPU: the SCM_RIGHTS file-descriptor exchange over abstract
+    unix datagram sockets (parallel/symm.py) delivers every rank's fd to every peer, twice in a row (tag check), and
+    the one-sender form used for the multicast handle."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from dist_tuto.pth_b200.parallel.symm import SymmWorld
+    w = SymmWorld.__new__(SymmWorld)                        # plumbing only: no CUDA context, no allocations
+    w.group, w.world, w.rank, w._tag = None, size, rank, 0
+    tok = [os.urandom(6).hex() if rank == 0 else None]
+    dist.broadcast_object_list(tok, src=0)
+    w._token = tok[0]
+    w._sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+    w._sock.bind(w._addr(rank))
+    w._sock.settimeout(60.0)
+    dist.barrier()
+    for round_ in range(2):
+        r_fd = os.memfd_create("b2-test")                   # shareable object, like a VMM allocation handle
+        os.write(r_fd, b"from-%d-round-%d" % (rank, round_))
+        got = w._exchange_fds(r_fd)                         # everyone sends its descriptor to everyone
+        os.close(r_fd)
+        assert sorted(got) == [r for r in range(size) if r != rank]
+        for src, fd in got.items():
+            assert os.pread(fd, 64, 0) == b"from-%d-round-%d" % (src, round_)  # the fd really is the sender's object
+            os.close(fd)
+    r_fd = os.memfd_create("b2-test-mc")
+    os.write(r_fd, b"mc-handle")
+    got = w._exchange_fds(r_fd, only_from=0)                # multicast-handle form: rank 0 -> all
+    os.close(r_fd)
+    if rank == 0:
+        assert got == {}
+    else:
+        assert list(got) == [0] and os.pread(got[0], 64, 0) == b"mc-handle"
+        os.close(got[0])
+    w._sock.close()
+
+
 def w_train(rank, size):
     ds = SyntheticMNIST(n=1024, seed=5)
     logs = []

@@ -66,3 +66,24 @@ def test_ddp_buckets_partition_the_parameters_in_reverse_order(shape_list, cap):
     for p in m.parameters():
         assert torch.allclose(p.grad, torch.full_like(p, 2.0))
     ddp.remove_hooks()
+
+
+def test_all_reduce_variant_table_matches_the_measured_thresholds():
+    """pick_variant(): the size -> kernel table measured on B200 (profiles/n2, profiles/n8), checked without a GPU."""
+    from dist_tuto.pth_b200.parallel.symm import SymmWorld, VARIANTS
+
+    def world(n, multicast):
+        w = SymmWorld.__new__(SymmWorld)
+        w.world, w.multicast = n, multicast
+        w.oneshot_max = (64 << 10) if n <= 2 else (8 << 10)
+        w.nvls_min = (1 << 62) if n <= 2 else (8 << 10) + 1
+        return w
+
+    one, two, nvls = VARIANTS["oneshot"], VARIANTS["twoshot"], VARIANTS["nvls"]
+    assert world(1, False).pick_variant(1 << 20) == one
+    w2 = world(2, True)
+    assert [w2.pick_variant(b) for b in (1 << 10, 64 << 10, (64 << 10) + 16, 1 << 30)] == [one, one, two, two]   # NVLS never at 2
+    w8 = world(8, True)
+    assert [w8.pick_variant(b) for b in (1 << 10, 8 << 10, (8 << 10) + 16, 87360, 1 << 30)] == [one, one, nvls, nvls, nvls]
+    w8n = world(8, False)                                   # switch without multicast objects: two-shot takes over
+    assert [w8n.pick_variant(b) for b in (1 << 10, 87360, 1 << 30)] == [one, two, two]

@@ -36,6 +36,10 @@ def test_flat_sgd_with_ddp_world2_equals_global_batch_sgd():
     go(W.w_flat_sgd_ddp, 2)
 
 
+def test_symmetric_memory_fd_exchange_world3():
+    go(W.w_symm_fd_exchange, 3)
+
+
 def test_train_loop_world2_replicas_identical():
     go(W.w_train, 2)
 
