@@ -61,5 +61,7 @@ if __name__ == "__main__":
 
     make_figs.make_all()
     src = open(os.path.join(HERE, "tutorial.md")).read()
-    open(os.path.join(HERE, "tutorial.html"), "w").write(render(src))
-    print("wrote docs/tutorial.html")
+    page = render(src)
+    for name in ("tutorial.html", "index.html"):       # the reference ships both tuto.html and index.html
+        open(os.path.join(HERE, name), "w").write(page)
+    print("wrote docs/tutorial.html, docs/index.html")
