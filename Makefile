@@ -23,6 +23,7 @@ bench:
 docs:
 	python docs/build_docs.py
 	python docs/build_api.py
+	python docs/build_pdf.py
 
 clean:
 	rm -rf dist_tuto.pth_b200/csrc/build dist_tuto.pth_b200/_C.so docs/tutorial.html

@@ -41,3 +41,19 @@ def test_api_reference_lists_every_tutorial_name(tmp_path, monkeypatch):
                  "gather", "all_gather", "reduce_op", "allreduce", "Partition", "DataPartitioner", "partition_dataset", "Net",
                  "average_gradients", "run"):
         assert f"`{name}" in text, name
+
+
+def test_pdf_is_structurally_valid():
+    import re
+    import build_pdf
+    pdf = build_pdf.build(open(os.path.join(ROOT, "docs", "tutorial.md")).read())
+    assert pdf.startswith(b"%PDF-1.4") and pdf.rstrip().endswith(b"%%EOF")
+    sx = int(re.search(rb"startxref\n(\d+)", pdf).group(1))
+    assert pdf[sx:sx + 4] == b"xref"
+    offsets = [int(o) for o in re.findall(rb"(\d{10}) 00000 n", pdf[sx:])]
+    for i, o in enumerate(offsets, 1):                      # every xref entry points at its object
+        assert pdf[o:].startswith(b"%d 0 obj" % i)
+    for m in re.finditer(rb"<< /Length (\d+) >>\nstream\n", pdf):   # stream lengths are exact
+        end = m.end() + int(m.group(1))
+        assert pdf[end:end + 10] == b"\nendstream"
+    assert pdf.count(b"/Type /Page /Parent") >= 3 and b"Distributed Training" in pdf
