@@ -31,7 +31,13 @@ def main():
         if obj is None:
             continue
         sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
-        open(os.path.join(OUT, stem + ".sass"), "w").write(sass)
+        # keep the listing readable and small: drop the hex encodings (second comment column and encoding-only lines)
+        slim = []
+        for ln in sass.splitlines():
+            ln = re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", ln)
+            if ln.strip():
+                slim.append(ln.rstrip())
+        open(os.path.join(OUT, stem + ".sass"), "w").write("\n".join(slim) + "\n")
         per_fn, cur = collections.OrderedDict(), None
         for ln in sass.splitlines():
             m = re.search(r"Function : (\S+)", ln)
