@@ -1,4 +1,5 @@
-"""Model check of the push ("flag-in-data") gradient exchange of csrc/sgd.cu, `allreduce_sgd_push_kernel`.
+"""Model checks of the two cross-GPU synchronisation protocols: the push ("flag-in-data") gradient exchange of csrc/sgd.cu
+(`allreduce_sgd_push_kernel`, first part) and the one-slot flag barrier of csrc/common.cuh (second part).
 
 The kernel's safety argument (SURVEY §7.4 hard part #1: no reset races across back-to-back steps) is: lines carry
 epoch = step + 1, inboxes are double-buffered by step parity, and a peer can only overwrite parity p two steps later --
@@ -129,3 +130,65 @@ def test_single_buffered_inbox_is_caught_by_the_model():
         if found:
             break
     assert found is not None and ("deadlock" in found or "consumed" in found)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The flag barrier of csrc/common.cuh (`block_barrier_all_ranks`): ONE slot per (block, source rank), monotonically
+# growing epochs, ">= epoch" wait.  Claim: one slot suffices because a peer can be at most one barrier ahead, and a rank
+# that passes barrier k knows every peer has ARRIVED at barrier k (so its writes before the barrier are visible).
+def run_barrier(world, rounds, choose, compare=lambda have, want: have >= want):
+    flags = [[0] * world for _ in range(world)]          # flags[dst][src]
+    arrived = [0] * world                                # highest barrier each rank has entered
+    epoch = [0] * world
+    todo = [[] for _ in range(world)]                    # pending stores of the barrier being executed
+    passed = [0] * world
+    for _ in range(200000):
+        if all(p == rounds for p in passed):
+            return None
+        runnable = []
+        for r in range(world):
+            if passed[r] == rounds:
+                continue
+            if epoch[r] == passed[r]:                    # not inside a barrier: enter the next one
+                runnable.append(r)
+            elif todo[r]:
+                runnable.append(r)
+            elif all(compare(flags[r][q], epoch[r]) for q in range(world)):
+                runnable.append(r)
+        if not runnable:
+            return "deadlock: passed=%s" % passed
+        r = choose(runnable)
+        if epoch[r] == passed[r]:
+            epoch[r] += 1
+            arrived[r] = epoch[r]
+            todo[r] = list(range(world))                 # signal every peer (and itself)
+        elif todo[r]:
+            flags[todo[r].pop(0)][r] = epoch[r]
+        else:
+            k = epoch[r]
+            if any(arrived[q] < k for q in range(world)):
+                return f"rank {r} passed barrier {k} before everybody arrived: {arrived}"
+            passed[r] = k
+    return "did not terminate"
+
+
+@pytest.mark.parametrize("world,rounds", [(2, 6), (3, 5), (8, 4)])
+def test_flag_barrier_with_one_slot_per_source_is_safe(world, rounds):
+    for seed in range(300):
+        rng = random.Random(seed * 104729 + world)
+        weights = [rng.choice([1, 1, 5, 25]) for _ in range(world)]
+        bad = run_barrier(world, rounds, lambda rs: rng.choices(rs, weights=[weights[r] for r in rs])[0])
+        assert bad is None, (seed, bad)
+
+
+def test_flag_barrier_needs_the_monotonic_compare():
+    """With an equality wait a fast peer that is already one barrier ahead overwrites the slot and the slow rank never
+    sees 'its' epoch: the model must find the hang.  (The kernel waits for `>= epoch`, wrap-safe.)"""
+    found = None
+    for seed in range(400):
+        rng = random.Random(seed)
+        weights = [25, 1, 1]
+        found = run_barrier(3, 5, lambda rs: rng.choices(rs, weights=[weights[r] for r in rs])[0], compare=lambda have, want: have == want)
+        if found:
+            break
+    assert found is not None and "deadlock" in found
