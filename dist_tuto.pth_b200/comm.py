@@ -49,6 +49,7 @@ class _World:
 
 
 class group:  # noqa: N801 - mirrors ``dist.group.WORLD`` (ptp.py:14)
+    """``dist.group.WORLD`` of the 2017 API (ptp.py:14): the default group, spelled ``None`` here."""
     WORLD = None
 
 
@@ -60,14 +61,17 @@ def _g(grp):
 
 
 def is_initialized() -> bool:
+    """True inside ``init_processes`` / after ``init_process_group`` (single-process use is allowed: rank 0 of 1)."""
     return dist.is_available() and dist.is_initialized()
 
 
 def get_rank(group=None) -> int:
+    """``dist.get_rank()`` (tuto.md:46, ptp.py:22); 0 when no process group exists."""
     return dist.get_rank(_g(group)) if is_initialized() else 0
 
 
 def get_world_size(group=None) -> int:
+    """``dist.get_world_size()`` (train_dist.py:84,95; ptp.py:23); 1 when no process group exists."""
     return dist.get_world_size(_g(group)) if is_initialized() else 1
 
 
@@ -101,6 +105,8 @@ class Request:
         self._tensor = tensor
 
     def wait(self, sync: bool = False) -> bool:
+        """``req.wait()`` of tuto.md:108-116: after it the buffer may be reused (send) / read (recv).  On CUDA the
+        transfer is ordered on the current stream; ``sync=True`` additionally blocks the host until it has finished."""
         if self._work is not None:
             self._work.wait()
             self._work = None
@@ -109,6 +115,7 @@ class Request:
         return True
 
     def is_completed(self) -> bool:
+        """Non-blocking completion test."""
         return self._work is None or self._work.is_completed()
 
 
@@ -223,6 +230,8 @@ def all_gather(tensor_list: List[torch.Tensor], tensor: torch.Tensor, group=None
 
 
 def barrier(group=None):
+    """Block until every rank of ``group`` got here (absent from the reference, which never synchronises explicitly --
+    SURVEY §5; used by tests, benches and the symmetric-memory setup).  No-op without a process group."""
     g = _g(group)
     if not is_initialized():
         return

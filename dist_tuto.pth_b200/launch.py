@@ -52,6 +52,7 @@ class LaunchError(RuntimeError):
 
 
 def find_free_port(addr: str = DEFAULT_ADDR) -> int:
+    """A currently free TCP port on ``addr`` (the reference hard-codes 29500, train_dist.py:133)."""
     with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
         s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
         s.bind((addr, 0))

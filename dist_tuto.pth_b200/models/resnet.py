@@ -21,6 +21,7 @@ __all__ = ["ResNet18", "BasicBlock"]
 
 
 class BasicBlock(nn.Module):
+    """conv3x3-BN-ReLU-conv3x3-BN + identity / 1x1 downsample (torchvision parameter names)."""
     expansion = 1
 
     def __init__(self, cin: int, cout: int, stride: int = 1):
@@ -41,6 +42,10 @@ class BasicBlock(nn.Module):
 
 
 class ResNet18(nn.Module):
+    """The larger-gradient model of BASELINE config #3 (11,689,512 parameters at 1000 classes; state_dict keys match
+    torchvision's ``resnet18``).  Only its gradients matter here: 45 MB in ~60 tensors exercise the bucketed, overlapped
+    all-reduce.  ``use_tc_fc`` routes the inference-time classifier through the tcgen05 GEMM."""
+
     def __init__(self, num_classes: int = 1000, in_channels: int = 3, use_tc_fc: bool = False):
         super().__init__()
         self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)

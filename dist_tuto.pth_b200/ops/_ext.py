@@ -18,10 +18,12 @@ _lock = threading.Lock()
 
 
 def so_path() -> str:
+    """Path of the in-tree extension (``dist_tuto.pth_b200/_C.so``; built by ``build.py``)."""
     return _SO
 
 
 def available() -> bool:
+    """Whether the native extension can be loaded (building it first if allowed)."""
     try:
         C()
         return True

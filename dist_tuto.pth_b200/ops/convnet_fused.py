@@ -369,6 +369,7 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ nn.Module-like surface
     def train(self, mode: bool = True):
+        """``model.train()`` / ``model.eval()``: dropout on/off (captured graphs are dropped, the flag is baked in)."""
         if mode != self.training:
             self.sync_lag(0)
             self.training = mode
@@ -377,9 +378,11 @@ class FusedTrainer:
         return self
 
     def eval(self):
+        """``model.eval()``."""
         return self.train(False)
 
     def parameters(self):
+        """Views of the flat fp32 parameter buffer, in the reference ``Net``'s order (train_dist.py:53-62)."""
         return list(unpack_params(self.params).values())
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
@@ -391,6 +394,7 @@ class FusedTrainer:
         return convnet_forward(self.params, x)
 
     def state_dict(self):
+        """``{'model': ..., 'momentum': ..., 'steps': ...}`` with the reference's parameter names (CPU copies)."""
         self.sync_lag(0)
         self.stream.synchronize()
         p, m = unpack_params(self.params), unpack_params(self.momentum)
@@ -399,6 +403,8 @@ class FusedTrainer:
                 "steps": int(self.step_counter.item()), "lr": self.lr, "mu": self.mu}
 
     def load_state_dict(self, sd):
+        """Accepts a trainer checkpoint or a plain ``Net`` state_dict.  Collective when ``steps`` is present (the bucket
+        parity and the exchange epochs derive from the step counter, see :meth:`_reset_exchange`)."""
         self.sync_lag(0)
         model = sd.get("model", sd)
         views = unpack_params(self.params)

@@ -69,6 +69,8 @@ class FlatSGD:
 
     @torch.no_grad()
     def step(self) -> None:
+        """``optimizer.step()`` (train_dist.py:124) for every bucket, and -- with ``zero_grad=True`` -- the
+        ``optimizer.zero_grad()`` of the next iteration (train_dist.py:118) in the same pass."""
         for gb, pf, mf in zip(self.buckets, self.param_flats, self.momentum_flats):
             g = gb.flat
             if pf.is_cuda and g.dtype == torch.float32:
@@ -86,6 +88,7 @@ class FlatSGD:
             self._engine._reset()
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002 - gradients stay views of the bucket
+        """Loop-compatibility call (train_dist.py:118): the buckets are already zero after ``step()``; re-arms the DDP hooks."""
         if self._engine is not None:
             self._engine.zero_grad() if not self.fused_zero else self._engine._reset()
         elif not self.fused_zero:
@@ -94,10 +97,12 @@ class FlatSGD:
 
     # ------------------------------------------------------------------ checkpointing
     def state_dict(self) -> dict:
+        """Hyper-parameters + the flat momentum buffers (CPU copies), for ``utils.checkpoint.save_checkpoint``."""
         return {"lr": self.lr, "momentum": self.momentum, "weight_decay": self.weight_decay,
                 "momentum_buffers": [m.detach().cpu().clone() for m in self.momentum_flats]}
 
     def load_state_dict(self, sd: dict) -> None:
+        """Inverse of :meth:`state_dict` (same model => same bucket layout)."""
         self.lr, self.momentum, self.weight_decay = float(sd["lr"]), float(sd["momentum"]), float(sd["weight_decay"])
         for m, src in zip(self.momentum_flats, sd["momentum_buffers"]):
             m.copy_(src)

@@ -101,6 +101,7 @@ class GradBucket:
             p.grad = v
 
     def zero_(self) -> None:
+        """``optimizer.zero_grad()`` for the bucket: one memset of the flat buffer; re-attaches detached ``p.grad``."""
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
@@ -119,6 +120,7 @@ class GradBucket:
 
 
 def flatten_params(model: nn.Module) -> List[nn.Parameter]:
+    """The trainable parameters in definition order (what ``model.parameters()`` of train_dist.py:97 iterates)."""
     return [p for p in model.parameters() if p.requires_grad]
 
 
@@ -243,9 +245,11 @@ class DistributedDataParallel(nn.Module):
 
     @property
     def buckets(self) -> List[GradBucket]:
+        """The flat gradient buckets, in the order backward completes them."""
         return [b.gb for b in self._buckets]
 
     def forward(self, *a, **kw):
+        """Runs the wrapped module; gradient communication is driven by the hooks during ``backward()``."""
         return self.module(*a, **kw)
 
     # -- per-step state -----------------------------------------------------
@@ -255,6 +259,7 @@ class DistributedDataParallel(nn.Module):
             b.launched = False
 
     def zero_grad(self, set_to_none: bool = False):  # noqa: ARG002 - grads stay views
+        """Zero every bucket (gradients stay views of the flat buffers) and re-arm the per-step hook bookkeeping."""
         for b in self._buckets:
             b.gb.zero_()
         self._reset()
@@ -293,6 +298,7 @@ class DistributedDataParallel(nn.Module):
         self._reset()
 
     def remove_hooks(self):
+        """Detach the engine from the module (hooks and the ``_ddp_engine`` back-reference)."""
         for h in self._hooks:
             h.remove()
         self._hooks = []

@@ -62,6 +62,7 @@ class SymmHandle:
         self.dtype = None
 
     def view(self, dtype, numel=None) -> torch.Tensor:
+        """This rank's buffer as a 1-D tensor of ``dtype`` (no ownership: the handle keeps the mapping alive)."""
         es = torch.empty((), dtype=dtype).element_size()
         n = self.nbytes // es if numel is None else numel
         return _ext.C().tensor_from_ptr(self.ptrs[self.world.rank], n, dtype, self.world.device.index)
@@ -225,6 +226,8 @@ class SymmWorld:
         return mc, C.symm_map(dev, mc, size, self.gran)
 
     def alloc(self, numel: int, dtype: torch.dtype) -> SymmHandle:
+        """Collective: a symmetric buffer of ``numel`` elements (padded to 64) on every rank; ``handle.local`` is this
+        rank's tensor, ``handle.ptrs`` the same buffer of every rank as mapped into THIS process."""
         es = torch.empty((), dtype=dtype).element_size()
         numel_p = (numel + 63) // 64 * 64
         hd = self.alloc_bytes(numel_p * es)
@@ -235,9 +238,12 @@ class SymmWorld:
 
     # ------------------------------------------------------------------ collectives
     def supports(self, t: torch.Tensor) -> bool:
+        """Can ``all_reduce_`` take this tensor (CUDA, this device, fp32/bf16, contiguous)?"""
         return t.is_cuda and t.device == self.device and t.dtype in _DTYPES and t.is_contiguous()
 
     def pick_variant(self, wire_bytes: int) -> int:
+        """Message size -> kernel (0 one-shot, 1 two-shot, 2 NVLS) from the measured thresholds; ``B200DIST_AR_VARIANT``
+        forces one."""
         if self.world == 1:
             return 0
         forced = os.environ.get("B200DIST_AR_VARIANT")
@@ -307,15 +313,18 @@ class SymmWorld:
         return st
 
     def barrier(self, handle: Optional[SymmHandle] = None):
+        """Device-side barrier over the world (flag kernel on the current stream; no host synchronisation)."""
         hd = handle or self._staging_for(torch.float32, 1 << 20)
         if self.world > 1:
             self.C.barrier(hd.sig_ptrs, self.rank, self.world)
 
     def describe(self) -> dict:
+        """What was negotiated at setup (mapping mode, multicast, thresholds) -- recorded in bench / sweep outputs."""
         return {"world": self.world, "rank": self.rank, "mode": self.mode, "multicast": self.multicast,
                 "granularity": self.gran, "nvls_error": self.nvls_error, "oneshot_max": self.oneshot_max}
 
     def destroy(self):
+        """Unmap and release every symmetric allocation of this world (idempotent; called by ``launch.shutdown``)."""
         try:
             torch.cuda.synchronize(self.device)
         except Exception:
@@ -355,10 +364,12 @@ def init_world(group=None, **kw) -> SymmWorld:
 
 
 def lookup_world(group=None) -> Optional[SymmWorld]:
+    """The symmetric world already built over ``group`` (``None`` = default group), or ``None``."""
     return _WORLDS.get(group)
 
 
 def destroy_all():
+    """Tear down every symmetric world of this process."""
     for w in list(_WORLDS.values()):
         w.destroy()
     _WORLDS.clear()

@@ -15,6 +15,7 @@ __all__ = ["save_checkpoint", "load_checkpoint"]
 
 
 def save_checkpoint(path: str, model, optimizer=None, **extra: Any) -> str:
+    """Atomically write ``model`` (module or fused trainer), ``optimizer`` state and ``extra`` keys to ``path``."""
     sd = model.state_dict()
     if "model" in sd and isinstance(sd.get("model"), dict):   # fused trainer: already structured
         blob: Dict[str, Any] = dict(sd)

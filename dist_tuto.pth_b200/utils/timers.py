@@ -24,6 +24,8 @@ __all__ = ["DeviceTimer", "PhaseTimers", "nvtx_range", "ClockSampler", "l2_flush
 
 
 class DeviceTimer:
+    """CUDA-event stopwatch on the current stream (``perf_counter`` on CPU)."""
+
     def __init__(self, device=None):
         self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
         self._t0 = self._e0 = self._e1 = None
@@ -46,6 +48,7 @@ class DeviceTimer:
 
 
 def max_over_ranks(value: float, device=None) -> float:
+    """MAX over ranks of a per-rank time: the number every multi-GPU measurement reports."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
@@ -56,6 +59,8 @@ def max_over_ranks(value: float, device=None) -> float:
 
 
 class PhaseTimers:
+    """Named device-timed phases with NVTX ranges: ``with timers.phase('allreduce'): ...``."""
+
     def __init__(self):
         self.ms: Dict[str, List[float]] = {}
 
@@ -72,6 +77,7 @@ class PhaseTimers:
 
 @contextlib.contextmanager
 def nvtx_range(name: str):
+    """NVTX push/pop around a block (no-op without CUDA)."""
     on = torch.cuda.is_available()
     if on:
         torch.cuda.nvtx.range_push(name)
