@@ -29,13 +29,13 @@ def test_fused_trainer_equals_global_batch_sgd():
     go(W.w_fused_trainer)
 
 
-def test_push_exchange_equals_barrier_exchange():
-    go(W.w_push_exchange_equals_barrier_exchange)
-
-
 def test_nccl_p2p_and_ring_allreduce():
     go(W.w_p2p_ring_gpu)
 
 
 def test_train_loop_fused_engine():
     go(W.w_train_fused_e2e)
+
+
+def test_push_exchange_equals_barrier_exchange():
+    go(W.w_push_exchange_equals_barrier_exchange)
