@@ -11,9 +11,9 @@ momentum 0.5, dropout on, synthetic 28x28 data, random-init weights.
 ``value``  : device-timed (CUDA events, max over ranks) training throughput of the fused engine -- full step =
              forward + loss + backward + peer-memory gradient all-reduce + SGD, nothing skipped -- on batches
              cycling through a device pool larger than L2.
-``e2e``    : the same metric through the public API a user calls (``partition_dataset()`` -> loader ->
-             ``FusedTrainer.step``): every step copies its batch from pinned host memory to the device and
-             copies the running loss back to pinned host memory.
+``e2e``    : the same metric through the public API a user calls (``partition_dataset()`` -> native loader ->
+             ``FusedTrainer.run_native``, i.e. what ``train()`` runs per epoch): every step copies its batch (uint8
+             pixels + labels) from pinned host memory to the device and the running loss back to pinned host memory.
 """
 from __future__ import annotations
 
