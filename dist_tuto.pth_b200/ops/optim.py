@@ -72,7 +72,7 @@ class FlatSGD:
         """``optimizer.step()`` (train_dist.py:124) for every bucket, and -- with ``zero_grad=True`` -- the
         ``optimizer.zero_grad()`` of the next iteration (train_dist.py:118) in the same pass."""
         for gb, pf, mf in zip(self.buckets, self.param_flats, self.momentum_flats):
-            g = gb.flat
+            g = gb.flat[:gb.numel]       # a symmetric-memory bucket is padded beyond the laid-out elements
             if pf.is_cuda and g.dtype == torch.float32:
                 self._kernel().sgd_flat(pf, mf, g, self.lr, self.momentum, self.weight_decay, self.fused_zero)
                 continue

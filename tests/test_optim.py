@@ -110,3 +110,23 @@ def test_flat_sgd_with_ddp_buckets_resnet_channels_last_gpu():
             opt.step()
     for (n, a), b in zip(ref.named_parameters(), ours.parameters()):
         assert torch.allclose(a, b, atol=2e-3, rtol=2e-2), n
+
+
+def test_flat_sgd_with_a_padded_bucket_buffer():
+    """Buckets that live in symmetric memory are padded (64-element granularity): the optimizer must only touch the
+    laid-out prefix.  Emulated on CPU by swapping in a longer flat buffer."""
+    ref, ours, o_ref, o_ours, xs, ys = _pair(torch.device("cpu"), 0.0)
+    gb = o_ours.buckets[0]
+    padded = torch.zeros(gb.numel + 40)
+    gb.flat = padded
+    gb.views = [padded[o:o + p.numel()].view(p.shape) for o, p in zip(gb.offsets, gb.params)]
+    for p in gb.params:
+        p.grad = None
+    gb.attach()
+    gb.zero_()
+    padded[gb.numel:] = 123.0                      # garbage in the padding must be neither read nor cleared
+    l_ref, l_ours = _steps(ref, o_ref, xs, ys), _steps(ours, o_ours, xs, ys)
+    assert l_ref == pytest.approx(l_ours, rel=1e-5)
+    for a, b in zip(ref.parameters(), ours.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert bool((padded[gb.numel:] == 123.0).all()) and float(padded[:gb.numel].abs().max()) == 0.0
