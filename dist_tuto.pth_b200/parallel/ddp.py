@@ -53,6 +53,13 @@ class GradBucket:
         self.group = group
         dev = self.params[0].device
         self.dtype = dtype or self.params[0].dtype
+        for p in self.params:
+            # reduced-precision gradient bucket (e.g. bf16 on the wire for fp32 master weights): autograd accumulates
+            # straight into the bucket's dtype when the parameter says so (torch >= 2.x `Tensor.grad_dtype`)
+            if p.dtype != self.dtype:
+                if not hasattr(p, "grad_dtype"):
+                    raise RuntimeError("a gradient bucket dtype different from the parameter dtype needs Tensor.grad_dtype")
+                p.grad_dtype = self.dtype
         self.offsets, n = [], 0
         for p in self.params:
             if p.device != dev:

@@ -193,6 +193,31 @@ def w_flat_sgd_ddp(rank, size):
     other = flat.clone()
     b2.broadcast(other, src=0)
     assert torch.equal(flat, other)                        # replicas identical
+    ddp.remove_hooks()
+    # bf16 gradients on the wire, fp32 master weights: same loop, looser tolerance, replicas still identical
+    torch.manual_seed(7)
+    ref2 = b2.Net().eval()
+    mine2 = b2.Net().eval()
+    mine2.load_state_dict({k: v.clone() for k, v in ref2.state_dict().items()})
+    ddp2 = DistributedDataParallel(mine2, bucket_cap_bytes=16384, grad_dtype=torch.bfloat16)
+    opt2 = b2.FlatSGD(ddp2, lr=0.05, momentum=0.5)
+    ref_opt2 = torch.optim.SGD(ref2.parameters(), lr=0.05, momentum=0.5)
+    for it in range(3):
+        g = torch.Generator().manual_seed(300 + it)
+        x, y = torch.randn(8 * size, 1, 28, 28, generator=g), torch.randint(0, 10, (8 * size,), generator=g)
+        opt2.zero_grad()
+        F.nll_loss(ddp2(x[rank * 8:(rank + 1) * 8]), y[rank * 8:(rank + 1) * 8]).backward()
+        b2.average_gradients(mine2)
+        opt2.step()
+        ref_opt2.zero_grad()
+        F.nll_loss(ref2(x), y).backward()
+        ref_opt2.step()
+    for (n, a), b in zip(ref2.named_parameters(), mine2.parameters()):
+        assert torch.allclose(a, b, atol=3e-3, rtol=3e-2), n
+    flat = torch.cat([p.detach().reshape(-1) for p in mine2.parameters()])
+    other = flat.clone()
+    b2.broadcast(other, src=0)
+    assert torch.equal(flat, other)
 
 
 def w_symm_fd_exchange(rank, size):

@@ -87,3 +87,32 @@ def test_all_reduce_variant_table_matches_the_measured_thresholds():
     assert [w8.pick_variant(b) for b in (1 << 10, 8 << 10, (8 << 10) + 16, 87360, 1 << 30)] == [one, one, nvls, nvls, nvls]
     w8n = world(8, False)                                   # switch without multicast objects: two-shot takes over
     assert [w8n.pick_variant(b) for b in (1 << 10, 87360, 1 << 30)] == [one, two, two]
+
+
+def test_bf16_gradient_bucket_for_fp32_master_weights():
+    """`DistributedDataParallel(grad_dtype=torch.bfloat16)`: gradients are accumulated by autograd directly into a bf16
+    flat bucket (half the bytes on the wire), parameters and momentum stay fp32 (`FlatSGD` casts at the update)."""
+    import copy
+    import torch.nn.functional as F
+    import dist_tuto.pth_b200 as dist
+    torch.manual_seed(0)
+    ref = dist.Net().eval()
+    mine = copy.deepcopy(ref)
+    ddp = DistributedDataParallel(mine, bucket_cap_bytes=8192, broadcast=False, grad_dtype=torch.bfloat16)
+    assert all(b.flat.dtype == torch.bfloat16 for b in ddp.buckets) and len(ddp.buckets) > 1
+    opt = dist.FlatSGD(ddp, lr=0.05, momentum=0.5)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.5)
+    for i in range(3):
+        g = torch.Generator().manual_seed(i)
+        x, y = torch.randn(16, 1, 28, 28, generator=g), torch.randint(0, 10, (16,), generator=g)
+        for model, o in ((ref, ref_opt), (ddp, opt)):
+            o.zero_grad()
+            F.nll_loss(model(x), y).backward()
+            if model is ddp:
+                dist.average_gradients(mine)
+            o.step()
+    for p in mine.parameters():
+        assert p.dtype == torch.float32 and p.grad.dtype == torch.bfloat16
+    for (n, a), b in zip(ref.named_parameters(), mine.parameters()):
+        assert torch.allclose(a, b, atol=3e-3, rtol=3e-2), n          # bf16 gradients: ~3 significant digits
+    ddp.remove_hooks()
