@@ -90,3 +90,27 @@ class _nullctx:
 
     def __exit__(self, *a):
         return False
+
+
+def test_file_init_method_with_group_name(tmp_path):
+    go(W.w_env, 2, init_method=f"file://{tmp_path}/shared", group_name="job-a")     # tuto.md:437-448
+
+
+def test_multicast_and_unknown_init_methods_are_rejected_with_a_clear_error():
+    import importlib
+    L = importlib.import_module("dist_tuto.pth_b200.launch")     # (the package attribute `launch` is the function)
+    with pytest.raises(ValueError, match="multicast"):
+        L._init_method("tcp://[ff15:1e18:5d4c:4cf0:d02d:b659:53ba:b0a7]:23456", "127.0.0.1", 29500)   # tuto.md:452
+    with pytest.raises(ValueError, match="unsupported"):
+        L._init_method("zeromq://x", "127.0.0.1", 29500)
+    assert L._init_method("tcp://10.1.1.20:23456", "127.0.0.1", 29500) == "tcp://10.1.1.20:23456"       # tuto.md:432
+
+
+def test_mpi_backend_without_a_launcher_environment_fails_loudly(monkeypatch):
+    import importlib
+    L = importlib.import_module("dist_tuto.pth_b200.launch")     # (the package attribute `launch` is the function)
+    for k in ("RANK", "WORLD_SIZE", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_RANK", "PMI_SIZE", "SLURM_PROCID",
+              "SLURM_NTASKS"):
+        monkeypatch.delenv(k, raising=False)
+    with pytest.raises(RuntimeError, match="external launcher"):
+        L.init_processes(0, 0, lambda r, s: None, backend="mpi")
