@@ -190,11 +190,6 @@ def broadcast(tensor: torch.Tensor, src: int, group=None):
     return dist.broadcast(tensor, src=src, group=_g(group))
 
 
-def _emulate_scatter_gather(tensor) -> bool:
-    # NCCL implements scatter/gather natively since 2.x via grouped p2p in c10d.
-    return False
-
-
 def scatter(tensor: torch.Tensor, src: int = 0, scatter_list: Optional[List[torch.Tensor]] = None,
             group=None):
     """i-th element of ``scatter_list`` on ``src`` goes to rank i (tuto.md:200).
