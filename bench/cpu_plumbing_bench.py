@@ -90,7 +90,7 @@ def w_reference(rank, size):
 def w_ours(rank, size):
     a = _args()
     torch.set_num_threads(a["threads"])
-    train_set, bsz = b2.partition_dataset(b2.SyntheticMNIST(n=60000, seed=1234))
+    train_set, bsz = b2.partition_dataset(b2.SyntheticMNIST(n=60000, seed=1234), native=a["native"])
     torch.manual_seed(1234)
     model = b2.Net()
     b2.broadcast_parameters(model)
@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--size", type=int, default=2)
     ap.add_argument("--threads", type=int, default=2, help="torch intra-op threads per rank")
+    ap.add_argument("--python-loader", dest="native", action="store_false", help="vectorised Python loader instead of the C++ prefetch thread")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     os.environ["B2_BENCH_ARGS"] = json.dumps(vars(args))
@@ -143,7 +144,8 @@ def main():
             if ln.startswith("{"):
                 rows.append(json.loads(ln))
     res = {"config": "train_dist.py ConvNet on CPU/gloo world_size=%d, synthetic 28x28, global batch 128" % args.size,
-           "steps": args.steps, "warmup": args.warmup, "threads_per_rank": args.threads, "timing": "wall clock, max over ranks",
+           "steps": args.steps, "warmup": args.warmup, "threads_per_rank": args.threads,
+           "ours_loader": "C++ prefetch thread (NativeBatchLoader)" if args.native else "vectorised Python BatchLoader", "timing": "wall clock, max over ranks",
            "rows": rows}
     print(json.dumps(res, indent=1))
     if args.out:
