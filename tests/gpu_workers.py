@@ -230,3 +230,20 @@ def w_train_fused_e2e(rank, size):
     out = b2.train(rank, size, cfg)
     assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
     dist.barrier()
+
+
+def w_train_torch_engine_gpu(rank, size):
+    """The tutorial loop on torch CUDA ops (engine='torch'): gradients in ONE symmetric flat bucket averaged by the fused
+    peer-memory all-reduce, update + zero_grad by the `sgd_flat` kernel (`FlatSGD`).  Replicas stay bit-identical."""
+    from dist_tuto.pth_b200.data import SyntheticMNIST
+    ds = SyntheticMNIST(n=2048, seed=5)
+    cfg = b2.TrainConfig(epochs=2, dataset=ds, lr=0.1, engine="torch", log=lambda *a: None)
+    out = b2.train(rank, size, cfg)
+    assert out["loss"][-1] == out["loss"][-1] and out["loss"][-1] < out["loss"][0], out["loss"]
+    model = out["model"]
+    assert model._grad_bucket.world is not None and model._grad_bucket.flat.numel() >= model._grad_bucket.numel
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    other = flat.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(flat, other)
+    dist.barrier()

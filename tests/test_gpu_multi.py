@@ -39,3 +39,7 @@ def test_train_loop_fused_engine():
 
 def test_push_exchange_equals_barrier_exchange():
     go(W.w_push_exchange_equals_barrier_exchange)
+
+
+def test_train_loop_torch_engine_symmetric_bucket_and_flat_sgd():
+    go(W.w_train_torch_engine_gpu)
