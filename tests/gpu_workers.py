@@ -246,4 +246,29 @@ def w_train_torch_engine_gpu(rank, size):
     other = flat.clone()
     dist.broadcast(other, src=0)
     assert torch.equal(flat, other)
+    # generic model: bucketed overlapped DDP (symmetric, padded buckets) + FlatSGD, bf16 autocast, channels_last
+    from dist_tuto.pth_b200.models.resnet import ResNet18
+    dev = _dev()
+    torch.manual_seed(3 + rank)                                  # broadcast inside DDP must make the replicas equal
+    net = ResNet18(num_classes=10).to(dev).to(memory_format=torch.channels_last)
+    ddp = b2.DistributedDataParallel(net, bucket_cap_bytes=4 << 20)
+    opt = b2.FlatSGD(ddp, lr=0.01, momentum=0.5)
+    assert len(opt.buckets) > 1 and all(b.world is not None for b in opt.buckets)
+    for it in range(3):
+        g = torch.Generator().manual_seed(700 + it * size + rank)
+        x = torch.randn(8, 3, 64, 64, generator=g).to(dev).to(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (8,), generator=g).to(dev)
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(ddp(x), y)
+        loss.backward()
+        b2.average_gradients(net)
+        opt.step()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss))
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    other = flat.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(flat, other)
+    ddp.remove_hooks()
     dist.barrier()
