@@ -17,6 +17,7 @@ GREY = "#d0d0d0"
 class Svg:
     def __init__(self, w, h, title):
         self.w, self.h = w, h
+        self.prims = []          # the same drawing as plain primitives (PNG preview, see `preview_png`)
         self.parts = [
             f'<svg xmlns="http://www.w3.org/2000/svg" width="{w}" height="{h}" viewBox="0 0 {w} {h}" '
             f'font-family="Helvetica,Arial,sans-serif" font-size="13">',
@@ -28,33 +29,72 @@ class Svg:
 
     def box(self, x, y, w, h, fill, label="", stroke="#333", fg="white"):
         self.parts.append(f'<rect x="{x}" y="{y}" width="{w}" height="{h}" rx="4" fill="{fill}" stroke="{stroke}"/>')
+        self.prims.append(("rect", x, y, w, h, fill, stroke))
         if label:
             self.text(x + w / 2, y + h / 2 + 4, label, fg, "middle")
 
     def text(self, x, y, s, fill="#222", anchor="start", size=None, bold=False):
         extra = (f' font-size="{size}"' if size else "") + (' font-weight="bold"' if bold else "")
         self.parts.append(f'<text x="{x}" y="{y}" fill="{fill}" text-anchor="{anchor}"{extra}>{s}</text>')
+        self.prims.append(("text", x, y, s, fill, anchor, size or 13))
 
     def arrow(self, x1, y1, x2, y2, dash=False, color="#333"):
         d = ' stroke-dasharray="5,4"' if dash else ""
         self.parts.append(
             f'<line x1="{x1}" y1="{y1}" x2="{x2}" y2="{y2}" stroke="{color}" stroke-width="1.6"{d} marker-end="url(#arr)"/>')
+        self.prims.append(("line", x1, y1, x2, y2, color))
 
     def save(self, name):
         os.makedirs(OUT, exist_ok=True)
         path = os.path.join(OUT, name + ".svg")
         with open(path, "w") as f:
             f.write("\n".join(self.parts) + "\n</svg>\n")
+        if os.environ.get("FIGS_PNG_PREVIEW"):
+            preview_png(self, os.path.join(os.environ["FIGS_PNG_PREVIEW"], name + ".png"))
         return path
 
 
-def rank_row(s, y, cells, label=None, x0=70, cw=44, gap=130):
+def preview_png(svg: "Svg", path: str, scale: int = 2) -> None:
+    """Rasterise the drawing with PIL (approximate fonts) -- a way to LOOK at the figures where no SVG viewer exists."""
+    from PIL import Image, ImageDraw, ImageFont
+    img = Image.new("RGB", (svg.w * scale, svg.h * scale), "white")
+    d = ImageDraw.Draw(img)
+
+    def font(sz):
+        for cand in (os.environ.get("FIGS_PREVIEW_FONT"), "DejaVuSans.ttf"):
+            try:
+                if cand:
+                    return ImageFont.truetype(cand, int(sz * scale))
+            except OSError:
+                pass
+        return ImageFont.load_default()
+
+    import html as _html
+    for pr in svg.prims:
+        if pr[0] == "rect":
+            _, x, y, w, h, fill, stroke = pr
+            d.rectangle([x * scale, y * scale, (x + w) * scale, (y + h) * scale], fill=fill, outline=stroke)
+        elif pr[0] == "line":
+            _, x1, y1, x2, y2, color = pr
+            d.line([x1 * scale, y1 * scale, x2 * scale, y2 * scale], fill=color, width=scale)
+            d.ellipse([(x2 - 2.5) * scale, (y2 - 2.5) * scale, (x2 + 2.5) * scale, (y2 + 2.5) * scale], fill=color)
+        else:
+            _, x, y, t, fill, anchor, size = pr
+            f = font(size)
+            t = _html.unescape(t)
+            wpx = d.textlength(t, font=f)
+            x0 = x * scale - (wpx / 2 if anchor == "middle" else 0)
+            d.text((x0, (y - size) * scale), t, fill=fill, font=f)
+    img.save(path)
+
+
+def rank_row(s, y, cells, label=None, x0=70, cw=44, gap=130, labels_below=False):
     """One row of `len(cells)` ranks; cells[r] is a list of (color, text) slots held by rank r."""
     if label:
         s.text(8, y + 20, label, size=12)
     for r, slots in enumerate(cells):
         x = x0 + r * gap
-        s.text(x + (cw * max(1, len(slots))) / 2, y - 6, f"rank {r}", "#555", "middle", 11)
+        s.text(x + (cw * 0.62 * max(1, len(slots))) / 2, y + 44 if labels_below else y - 6, f"rank {r}", "#555", "middle", 11)
         if not slots:
             s.box(x, y, cw, 30, "white", "", GREY)
         for k, (c, t) in enumerate(slots):
@@ -63,10 +103,10 @@ def rank_row(s, y, cells, label=None, x0=70, cw=44, gap=130):
 
 def before_after(name, title, before, after, arrows):
     n = len(before)
-    s = Svg(90 + 130 * n, 210, title)
+    s = Svg(90 + 130 * n, 215, title)
     s.text(8, 18, title, bold=True, size=14)
     rank_row(s, 50, before, "before")
-    rank_row(s, 150, after, "after")
+    rank_row(s, 150, after, "after", labels_below=True)
     for a, b in arrows:
         s.arrow(70 + a * 130 + 20, 82, 70 + b * 130 + 20, 140)
     return s.save(name)
@@ -118,37 +158,41 @@ def make_all():
     s.text(280, 228, "chunked variant: reduce-scatter + all-gather, 2(N-1)/N x M bytes per rank", "#666", "middle", 11)
     paths.append(s.save("ring_allreduce"))
     # --- peer-memory variants
-    s = Svg(760, 300, "peer memory all-reduce")
+    s = Svg(760, 330, "peer memory all-reduce")
     s.text(8, 18, "fused all-reduce over symmetric peer memory (csrc/allreduce.cu)", bold=True, size=14)
     for r in range(4):
         s.box(40 + r * 180, 40, 140, 36, COL[r], f"GPU {r}: bucket[0..M)")
-    s.text(8, 110, "one-shot", bold=True)
-    s.text(90, 110, "every GPU reads all N buckets (ld.global over NVLink), sums in rank order, scales by 1/N, "
-           "writes its own copy:  N x M bytes in, 1 barrier pair", "#333", size=12)
-    s.text(8, 150, "two-shot", bold=True)
-    s.text(90, 150, "GPU r reduces slice r of every bucket, then stores the result into every peer's slice r:  "
-           "2 (N-1)/N x M bytes", "#333", size=12)
-    s.text(8, 190, "NVLS", bold=True)
-    s.text(90, 190, "multimem.ld_reduce on a multicast address: the NVSwitch adds the N copies in flight; "
-           "multimem.st broadcasts the result", "#333", size=12)
-    s.box(250, 215, 260, 34, "#333", "NVSwitch (in-switch fp32 add)")
-    for r in range(4):
-        s.arrow(110 + r * 180, 78, 300 + r * 50, 213, dash=True, color="#777")
-    s.text(380, 278, "barrier = per-block flags in each buffer's signal pad, st.release.sys / ld.acquire.sys, "
+        s.arrow(110 + r * 180, 78, 300 + r * 54, 108, dash=True, color="#777")
+    s.box(250, 110, 260, 34, "#333", "NVSwitch (NVLS: in-switch fp32 add)")
+    rows = [("one-shot", "every GPU reads all N buckets (ld.global over NVLink), sums in rank order, scales by 1/N,",
+             "writes its own copy: N x M bytes in, one barrier pair -- latency-optimal, small messages"),
+            ("two-shot", "GPU r reduces slice r of every bucket, then stores the result into every peer's slice r:",
+             "2 (N-1)/N x M bytes per GPU -- bandwidth-optimal without multicast"),
+            ("NVLS", "multimem.ld_reduce on a multicast address: the switch adds the N copies in flight;",
+             "multimem.st broadcasts the result -- M/N bytes read + M/N written per GPU")]
+    for i, (name, l1, l2) in enumerate(rows):
+        y = 176 + i * 44
+        s.text(8, y, name, bold=True)
+        s.text(90, y, l1, "#333", size=12)
+        s.text(90, y + 16, l2, "#333", size=12)
+    s.text(380, 318, "barrier = per-block flags in each buffer's signal pad, st.release.sys / ld.acquire.sys, "
            "monotonic epochs (CUDA-graph safe)", "#666", "middle", 11)
     paths.append(s.save("peer_allreduce"))
     # --- fused step
-    s = Svg(760, 170, "fused training step")
+    s = Svg(900, 210, "fused training step")
     s.text(8, 18, "one ConvNet training step = one CUDA graph (ops/convnet_fused.py)", bold=True, size=14)
-    xs = [(20, 120, GREY, "H2D batch (uint8)", "#222"), (160, 250, COL[0], "convnet_step: fwd+loss+bwd, red.add -> bucket", "white"),
-          (430, 190, COL[3], "allreduce + 1/N + SGD + zero", "white"), (640, 100, GREY, "D2H loss", "#222")]
-    for x, w, c, t, fg in xs:
+    boxes = [(20, 130, GREY, "H2D batch", "#222", ["uint8 pixels + labels from a", "pinned loader slot (copy stream)"]),
+             (190, 250, COL[0], "convnet_step", "white", ["forward + loss + backward, one CTA (or a 2/4/8-CTA", "cluster) per sample; red.add.v4 into the flat bucket"]),
+             (480, 250, COL[3], "allreduce_sgd", "white", ["push the bucket into the peers' inboxes (flag-in-data),", "sum in rank order, x 1/N, momentum SGD, re-zero"]),
+             (770, 110, GREY, "D2H loss", "#222", ["running loss to a", "pinned word"])]
+    for x, w, c, t, fg, desc in boxes:
         s.box(x, 50, w, 40, c, t, fg=fg)
-    for x in (142, 412, 622):
-        s.arrow(x, 70, x + 16, 70)
-    s.text(20, 120, "copy stream", "#666", size=11)
-    s.text(160, 120, "compute stream; kernel 2 pre-launched with programmatic dependent launch", "#666", size=11)
-    s.text(430, 140, "peer loads over NVSwitch; double-buffered bucket: one barrier per step", "#666", size=11)
+        for k, line in enumerate(desc):
+            s.text(x, 112 + 15 * k, line, "#555", size=11)
+    for x in (152, 442, 732):
+        s.arrow(x, 70, x + 36, 70)
+    s.text(190, 165, "kernel 2 is pre-launched under kernel 1 with programmatic dependent launch (griddepcontrol); the exchange", "#666", size=11)
+    s.text(190, 180, "crosses NVLink once: no barrier, no remote loads; gradient buckets and inboxes are double-buffered by step parity", "#666", size=11)
     paths.append(s.save("fused_step"))
     return paths
 
