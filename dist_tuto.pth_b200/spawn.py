@@ -42,13 +42,23 @@ def _stop(procs: Sequence[subprocess.Popen], grace_s: float = 5.0) -> None:
 
 def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, master_addr: str = DEFAULT_ADDR,
                master_port: Optional[int] = None, timeout_s: Optional[float] = None, env: Optional[dict] = None,
-               poll_s: float = 0.1) -> int:
-    """Run ``script`` as ``size`` ranks; returns the job's exit code (0 = every rank exited 0).
+               poll_s: float = 0.1, nnodes: int = 1, node_rank: int = 0) -> int:
+    """Run ``script`` as ``size`` local ranks; returns the job's exit code (0 = every rank exited 0).
+
+    Multi-machine jobs (the tutorial's "replace MASTER_ADDR by the IP of the master", tuto.md:404-428): start the launcher
+    once per machine with the same ``master_addr``/``master_port`` and ``nnodes``, and ``node_rank`` = 0..nnodes-1; global
+    rank = ``node_rank * size + local rank``.  (The ``b200`` backend's peer-memory world is one NVSwitch domain; use
+    ``nccl`` or ``gloo`` across machines.)
 
     Exit codes: the failing rank's own code; 124 on timeout (like ``timeout(1)``); 130 on interrupt."""
+    if nnodes > 1 and master_port is None:
+        raise ValueError("multi-node jobs need an explicit master_port (the same on every node)")
+    if not 0 <= node_rank < nnodes:
+        raise ValueError("node_rank must be in [0, nnodes)")
     port = master_port or find_free_port(master_addr)
     base = dict(os.environ if env is None else env)
-    base.update(WORLD_SIZE=str(size), MASTER_ADDR=master_addr, MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(size))
+    base.update(WORLD_SIZE=str(size * nnodes), MASTER_ADDR=master_addr, MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(size),
+                GROUP_RANK=str(node_rank))
     base.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, size))))
     procs: List[subprocess.Popen] = []
     interrupted = []
@@ -64,7 +74,7 @@ def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, mast
             pass
     try:
         for r in range(size):
-            e = dict(base, RANK=str(r), LOCAL_RANK=str(r))
+            e = dict(base, RANK=str(node_rank * size + r), LOCAL_RANK=str(r))
             procs.append(subprocess.Popen([sys.executable, script, *script_args], env=e))
         deadline = None if timeout_s is None else time.monotonic() + timeout_s
         while True:
@@ -95,15 +105,17 @@ def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, mast
 def main(argv: Optional[Sequence[str]] = None) -> int:
     ap = argparse.ArgumentParser(prog="python -m dist_tuto.pth_b200.spawn",
                                  description="start N ranks of a script that calls dist.init_from_env(run, backend)")
-    ap.add_argument("--size", "-n", type=int, default=2, help="world size (one process per rank / per GPU)")
+    ap.add_argument("--size", "-n", type=int, default=2, help="ranks on THIS machine (one process per rank / per GPU)")
     ap.add_argument("--master-addr", default=DEFAULT_ADDR)
     ap.add_argument("--master-port", type=int, default=None, help="default: a free port")
     ap.add_argument("--timeout", type=float, default=None, help="seconds for the whole job")
+    ap.add_argument("--nnodes", type=int, default=1, help="machines in the job (run the launcher once per machine)")
+    ap.add_argument("--node-rank", type=int, default=0, help="index of this machine, 0 = the one MASTER_ADDR points at")
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
     return run_script(a.script, a.script_args, size=a.size, master_addr=a.master_addr, master_port=a.master_port,
-                      timeout_s=a.timeout)
+                      timeout_s=a.timeout, nnodes=a.nnodes, node_rank=a.node_rank)
 
 
 if __name__ == "__main__":

@@ -44,3 +44,25 @@ def test_run_script_api_returns_zero(tmp_path):
     ok.write_text("import os, sys\nassert int(os.environ['WORLD_SIZE']) == 2 and os.environ['MASTER_ADDR'] == '127.0.0.1'\n"
                   "assert os.environ['RANK'] == os.environ['LOCAL_RANK']\n")
     assert run_script(str(ok), size=2, timeout_s=60) == 0
+
+
+def test_two_node_job_on_localhost():
+    """Two launchers = two 'machines' (tuto.md:404-428): 2 x 2 ranks rendezvous at one master, global ranks 0..3."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = str(s.getsockname()[1])
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+    nodes = [subprocess.Popen([sys.executable, "-m", "dist_tuto.pth_b200.spawn", "--size", "2", "--nnodes", "2", "--node-rank", str(n),
+                               "--master-port", port, "--timeout", "120", SCRIPT, "allreduce"], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT) for n in (0, 1)]
+    outs = [p.communicate(timeout=200) for p in nodes]
+    assert [p.returncode for p in nodes] == [0, 0], outs
+    lines = sorted(l for o, _ in outs for l in o.splitlines() if l.startswith("rank"))
+    assert lines == [f"rank {r} of 4 sum 10.0" for r in range(4)]
+
+
+def test_multi_node_needs_an_explicit_port():
+    from dist_tuto.pth_b200.spawn import run_script
+    with pytest.raises(ValueError, match="master_port"):
+        run_script(SCRIPT, ["allreduce"], size=1, nnodes=2, node_rank=0)
