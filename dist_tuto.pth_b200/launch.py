@@ -157,6 +157,7 @@ def init_processes(rank: int, size: int, fn: Callable[[int, int], object], backe
     try:
         if use_symm:
             from .parallel import symm
+            assert_one_node(backend)
             symm.init_world()
         return fn(rank, size)
     finally:
@@ -165,6 +166,18 @@ def init_processes(rank: int, size: int, fn: Callable[[int, int], object], backe
 
 
 init_process = init_processes  # BASELINE.json spelling
+
+
+def assert_one_node(backend: str = "b200") -> None:
+    """Collective: the peer-memory world maps every GPU's memory into every process, which only exists inside one
+    NVSwitch domain (one machine).  Fail with a clear message instead of a socket timeout deep in the setup."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    hosts = [None] * dist.get_world_size()
+    dist.all_gather_object(hosts, socket.gethostname())
+    if len(set(hosts)) > 1:
+        raise RuntimeError(f"backend '{backend}' builds a symmetric peer-memory world over NVSwitch, which spans ONE machine; "
+                           f"this job runs on {sorted(set(hosts))}.  Use backend='nccl' (or 'gloo') across machines.")
 
 
 def init_from_env(fn: Callable[[int, int], object], backend: str = "b200", **kw):

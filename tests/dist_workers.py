@@ -292,3 +292,22 @@ def w_env(rank, size):
     t = torch.ones(1)
     b2.all_reduce(t)
     assert t[0] == size
+
+
+def w_one_node_guard(rank, size):
+    """launch.assert_one_node(): passes on one host, raises a clear error when the ranks report different hosts."""
+    import importlib
+    import socket
+    L = importlib.import_module("dist_tuto.pth_b200.launch")
+    L.assert_one_node("b200")                              # same machine: fine
+    real = socket.gethostname
+    socket.gethostname = lambda: f"node-{rank}"            # pretend every rank sits on its own machine
+    try:
+        try:
+            L.assert_one_node("b200")
+        except RuntimeError as e:
+            assert "ONE machine" in str(e) and "node-0" in str(e) and "nccl" in str(e)
+        else:
+            raise AssertionError("multi-host symmetric world was not rejected")
+    finally:
+        socket.gethostname = real

@@ -114,3 +114,7 @@ def test_mpi_backend_without_a_launcher_environment_fails_loudly(monkeypatch):
         monkeypatch.delenv(k, raising=False)
     with pytest.raises(RuntimeError, match="external launcher"):
         L.init_processes(0, 0, lambda r, s: None, backend="mpi")
+
+
+def test_symmetric_backend_refuses_to_span_machines():
+    go(W.w_one_node_guard, 2)
