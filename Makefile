@@ -26,4 +26,4 @@ docs:
 	python docs/build_pdf.py
 
 clean:
-	rm -rf dist_tuto.pth_b200/csrc/build dist_tuto.pth_b200/_C.so docs/tutorial.html
+	rm -rf dist_tuto.pth_b200/csrc/build dist_tuto.pth_b200/_C.so
