@@ -18,6 +18,7 @@ Engines:
 """
 from __future__ import annotations
 
+import collections
 import time
 from math import ceil
 from typing import Callable, Optional
@@ -71,6 +72,7 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
                                        **({"raw_uint8": True} if fused_raw else {}))
     num_batches = ceil(len(train_set.dataset) / float(bsz))      # train_dist.py:112
     start_steps, optimizer, resume_blob = 0, None, {}
+    copies_in_flight = collections.deque()                       # torch engine on CUDA, see step_fn
     if engine == "fused":
         from .ops.convnet_fused import FusedTrainer
         trainer = FusedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
@@ -91,9 +93,21 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
             optimizer.load_state_dict(resume_blob["optim"])          # momentum buffers
         acc = torch.zeros((), device=device)
 
+        # The native loader recycles its pinned staging buffers; the async H2D copies below must have left a buffer
+        # before the prefetch thread refills it.  One event per handed-out batch, consumed in hand-out order.
+        if device.type == "cuda" and hasattr(train_set, "before_recycle"):
+            def _oldest_copy_done():
+                if copies_in_flight:
+                    copies_in_flight.popleft().synchronize()
+            train_set.before_recycle = _oldest_copy_done
+
         def step_fn(data, target):
             data = data.to(device, non_blocking=True)
             target = target.to(device, non_blocking=True)
+            if device.type == "cuda" and hasattr(train_set, "before_recycle"):
+                ev = torch.cuda.Event()
+                ev.record()
+                copies_in_flight.append(ev)
             optimizer.zero_grad()                                # buckets were re-zeroed by the previous step()
             output = model(data)
             loss = F.nll_loss(output, target)
@@ -113,6 +127,7 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     for epoch in range(cfg.epochs):
         model.train()
         nb = 0
+        copies_in_flight.clear()          # the previous epoch ended with a device sync (epoch_loss_fn): nothing is pending
         if native_loop:       # C++ executor: prefetch thread -> cudaGraphLaunch per step, no Python in the loop
             budget = None if cfg.max_steps is None else cfg.max_steps - steps
             nb, _ = trainer.run_native(train_set, max_steps=budget)
