@@ -53,41 +53,55 @@ def ours(args):
         dev = torch.device("cuda", torch.cuda.current_device())
         bsz = 128 // size
         tr = FusedTrainer(bsz, lr=0.01, momentum=0.5, seed=1234, device=dev, p_drop=0.5, raw_uint8=True)
-        # ------------------------------------------------------------ value: device-timed, pool > L2
+        # ------------------------------------------------------------ value: device-timed
+        # Layout of the measured stream (nothing but graph launches between the two events, no host sync inside):
+        #     [L2 flush] [pre-roll graph: G untimed steps] e0 [timed graphs: exactly K steps] e1
+        # * every graph is replayed once beforehand (upload + instantiate cost is not timed);
+        # * e0 is recorded ON THE STREAM behind the pre-roll steps: every step ends with the cross-GPU gradient
+        #   exchange, so by the time e0 fires all ranks are aligned to within one exchange and the host is already
+        #   ~G steps ahead with its launches -- inter-process start skew cannot sit inside e0 -> e1;
+        # * the batches of the timed graphs are not touched between the L2 flush (256 MB written) and their step.
         batch_bytes = bsz * 784 * 4
-        pool = max(8, (160 << 20) // batch_bytes)
         G = max(1, min(args.graph_chunk, K))
-        n_graphs = max(1, min(pool // G, 64))
-        pool = n_graphs * G
+        n_full, rem = divmod(K, G)
+        n_timed = min(n_full, 64)                    # graphs are reused round-robin beyond 64 chunks
+        n_graphs = n_timed + 1                       # + the pre-roll graph
+        pool = n_graphs * G + rem
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
         px = torch.randn(pool, bsz, 1, 28, 28, device=dev, generator=g)
         py = torch.randint(0, 10, (pool, bsz), device=dev, generator=g)
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         st = tr.stream
         with torch.cuda.stream(st):
             for i in range(W):
                 tr._kernels(px[i % pool], py[i % pool], bsz)
         st.synchronize()
-        graphs = []
-        for j in range(n_graphs):
+
+        def capture(first, count):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=st):
-                for i in range(G):
-                    tr._kernels(px[j * G + i], py[j * G + i], bsz)
-            graphs.append(gr)
+                for i in range(count):
+                    tr._kernels(px[first + i], py[first + i], bsz)
+            return gr
+
+        graphs = [capture(j * G, G) for j in range(n_graphs)]          # graphs[0] = pre-roll
+        tail = capture(n_graphs * G, rem) if rem else None
         with torch.cuda.stream(st):
-            graphs[0].replay()                                   # one untimed replay (graph upload)
+            for gr in graphs + ([tail] if tail is not None else []):   # untimed: uploads every graph that is timed later
+                gr.replay()
         st.synchronize()
         b2.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_full, rem = divmod(K, G)
         with ClockSampler(dev.index) as clk:
             with torch.cuda.stream(st):
+                flush_buf.fill_(1)                                     # L2 flush: 256 MB > 126 MB L2
+                graphs[0].replay()                                     # pre-roll (untimed)
                 e0.record(st)
                 for s in range(n_full):
-                    graphs[(s + 1) % n_graphs].replay()
-                for i in range(rem):
-                    tr._kernels(px[i], py[i], bsz)
+                    graphs[1 + s % n_timed].replay()
+                if tail is not None:
+                    tail.replay()
                 e1.record(st)
             st.synchronize()
             b2.barrier()
@@ -107,6 +121,8 @@ def ours(args):
             b2.barrier()
             clocks = dict(probe.summary(), in_timed_region=clocks["samples"],
                           note="timed region shorter than one nvidia-smi query; sampled while replaying the timed graphs right after it")
+        l2_note = (f"L2 flushed (256 MB written) right before the pre-roll; the K timed steps read {min(K, n_timed * G + rem)} distinct "
+                   f"batches ({min(K, n_timed * G + rem) * batch_bytes / 2**20:.1f} MB) not touched since the flush")
         loss_dev = float(tr.loss_acc[0].item())
         assert loss_dev == loss_dev, "loss is NaN"
 
@@ -147,7 +163,9 @@ def ours(args):
                                             "cluster_ctas_per_sample": tr.cluster,
                                             "gradient_exchange": ("push: flag-in-data stores into peer inboxes, local reduce" if tr.inbox_handle is not None
                                                                   else ("barrier + peer loads" if size > 1 else "none (1 GPU)")),
-                                            "l2": f"inputs cycle through a {pool * batch_bytes >> 20} MB device pool (> 126 MB L2)",
+                                            "l2": l2_note,
+                                            "timing": "CUDA events on the launch stream: [L2 flush][pre-roll graph, untimed] e0 [K steps] e1, "
+                                                      "enqueued back to back; max over ranks",
                                             "graph_chunk": G, "symm": sym,
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
                                                         "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "

@@ -92,10 +92,12 @@ def build(verbose: bool = True, force: bool = False) -> str:
     prev = open(stamp).read().strip() if os.path.exists(stamp) else ""
     if force or jobs or not os.path.exists(TARGET) or prev != link_tag:
         lib_dirs = ce.library_paths() + [os.path.join(cuda, "lib64")]
-        cmd = ["g++", "-shared", "-o", TARGET] + objs + [f"-L{d}" for d in lib_dirs] + \
+        tmp_target = f"{TARGET}.tmp{os.getpid()}"
+        cmd = ["g++", "-shared", "-o", tmp_target] + objs + [f"-L{d}" for d in lib_dirs] + \
               [f"-Wl,-rpath,{d}" for d in lib_dirs] + \
               ["-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart", "-lpthread"]
         _run(cmd, os.path.join(OBJ, "link.log"))
+        os.replace(tmp_target, TARGET)              # atomic: a concurrent importer sees the old or the new library, never half
         with open(stamp, "w") as f:
             f.write(link_tag)
         if verbose:
@@ -108,6 +110,35 @@ def build(verbose: bool = True, force: bool = False) -> str:
             if os.path.exists(os.path.join(OBJ, f + ".log")):
                 os.remove(os.path.join(OBJ, f + ".log"))
     return TARGET
+
+
+def _expected_objects():
+    """(object paths, link tag) the current sources/flags hash to -- without compiling anything."""
+    import torch
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cxx_flags = ["-O2", "-std=c++17", "-fPIC", "-Wno-unused-result", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
+                 "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    objs = []
+    for src in CU_SOURCES:
+        tag = _hash([os.path.join(CSRC, src)] + hdrs, " ".join(ARCH + NVCC_FLAGS))
+        objs.append(os.path.join(OBJ, f"{src}.{tag}.o"))
+    for src in CPP_SOURCES:
+        tag = _hash([os.path.join(CSRC, src)] + hdrs, " ".join(cxx_flags) + torch.__version__)
+        objs.append(os.path.join(OBJ, f"{src}.{tag}.o"))
+    return objs
+
+
+def up_to_date() -> bool:
+    """True when ``_C.so`` was linked from objects matching the CURRENT sources, headers and flags (content hashes)."""
+    try:
+        objs = _expected_objects()
+        if not os.path.isfile(TARGET) or not all(os.path.exists(o) for o in objs):
+            return False
+        stamp = os.path.join(OBJ, "link.stamp")
+        return os.path.exists(stamp) and open(stamp).read().strip() == _hash(objs, "link")
+    except Exception:
+        return False
 
 
 def ptxas_report() -> str:

@@ -299,7 +299,9 @@ class NativeBatchLoader:
         idx = partition.index_tensor() if isinstance(partition, Partition) else torch.arange(len(partition))
         pin = torch.cuda.is_available() if pin_memory is None else pin_memory
         seed = int(torch.initial_seed()) & 0x7FFFFFFF if seed is None else seed
-        self.num_buffers = max(3, num_buffers)
+        # >= 4: FusedTrainer.step() adopts these pinned buffers as graph H2D sources and keeps up to 2 steps in flight, so a
+        # slot may only be refilled 3 yields later (with 3 buffers batch 0's captured copy could still be pending)
+        self.num_buffers = max(4, num_buffers)
         self._l = _ext.C().NativeLoader(base.images, base.labels, idx, self.batch_size, self.num_buffers, shuffle,
                                         drop_last, raw_uint8, base.mean, base.std, seed, pin)
         self._epoch = 0

@@ -31,6 +31,31 @@ def available() -> bool:
         return False
 
 
+def _build_locked():
+    """(Re)build ``_C.so`` if it is missing or stale, serialised ACROSS processes.
+
+    N spawned ranks all land here at once: an ``flock`` on ``csrc/build/.lock`` lets one of them build while the others
+    wait and then find an up-to-date library.  ``build.build()`` is content-hashed (no-op when sources, flags and the
+    link stamp match) and links to a temporary file that is ``os.replace``d into place, so nobody can import a
+    half-written library.  When nvcc is not installed (a deployment box) an existing library is used as is."""
+    import fcntl
+    import shutil
+    from .. import build as _b
+    have_nvcc = os.path.exists(os.path.join(_b._cuda_home(), "bin", "nvcc")) or shutil.which("nvcc") is not None
+    if not have_nvcc:
+        if os.path.isfile(_SO):
+            return
+        raise ImportError(f"native extension missing and no nvcc to build it: {_SO}")
+    os.makedirs(_b.OBJ, exist_ok=True)
+    with open(os.path.join(_b.OBJ, ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not os.path.isfile(_SO) or not _b.up_to_date():
+                _b.build(verbose=False)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
 def C():
     """Return the loaded extension module (loads it on first use)."""
     global _mod, _err
@@ -39,13 +64,11 @@ def C():
     with _lock:
         if _mod is not None:
             return _mod
-        if not os.path.isfile(_SO):
-            if os.environ.get("B200DIST_AUTOBUILD", "1") == "1":       # build the real thing (never a PyTorch fallback)
-                from .. import build as _b
-                _b.build(verbose=False)
-            else:
-                raise ImportError(f"native extension missing: {_SO}\n"
-                                  "build it with:  python -c 'import __graft_entry__ as g; g.build()'")
+        if os.environ.get("B200DIST_AUTOBUILD", "1") == "1":           # build the real thing (never a PyTorch fallback)
+            _build_locked()
+        elif not os.path.isfile(_SO):
+            raise ImportError(f"native extension missing: {_SO}\n"
+                              "build it with:  python -c 'import __graft_entry__ as g; g.build()'")
         import torch  # noqa: F401  (libtorch must be loaded first)
         spec = importlib.util.spec_from_file_location("dist_tuto.pth_b200._C", _SO)
         mod = importlib.util.module_from_spec(spec)

@@ -101,6 +101,30 @@ class FlatSGD:
         return {"lr": self.lr, "momentum": self.momentum, "weight_decay": self.weight_decay,
                 "momentum_buffers": [m.detach().cpu().clone() for m in self.momentum_flats]}
 
+    def named_momentum(self, model: nn.Module) -> dict:
+        """Momentum per parameter NAME (CPU copies) -- the canonical, engine-independent form written to checkpoints: the
+        fused trainer stores exactly this (``state_dict()['momentum']``), so checkpoints cross engines with momentum."""
+        names = {id(p): n for n, p in getattr(model, "module", model).named_parameters()}
+        out = {}
+        for gb, mf in zip(self.buckets, self.momentum_flats):
+            for p, o, gv in zip(gb.params, gb.offsets, gb.views):
+                if id(p) in names:
+                    out[names[id(p)]] = mf[o:o + p.numel()].as_strided(gv.shape, gv.stride()).detach().cpu().clone()
+        return out
+
+    @torch.no_grad()
+    def load_named_momentum(self, model: nn.Module, named: dict) -> int:
+        """Inverse of :meth:`named_momentum`; returns how many tensors were restored."""
+        names = {id(p): n for n, p in getattr(model, "module", model).named_parameters()}
+        done = 0
+        for gb, mf in zip(self.buckets, self.momentum_flats):
+            for p, o, gv in zip(gb.params, gb.offsets, gb.views):
+                src = named.get(names.get(id(p)))
+                if src is not None:
+                    mf[o:o + p.numel()].as_strided(gv.shape, gv.stride()).copy_(src)
+                    done += 1
+        return done
+
     def load_state_dict(self, sd: dict) -> None:
         """Inverse of :meth:`state_dict` (same model => same bucket layout)."""
         self.lr, self.momentum, self.weight_decay = float(sd["lr"]), float(sd["momentum"]), float(sd["weight_decay"])

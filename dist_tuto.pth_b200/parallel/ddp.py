@@ -139,7 +139,10 @@ def average_gradients(model: nn.Module, group=None) -> None:
       bucketed all-reduce;
     * any other model: gradients are coalesced into one flat message (one
       collective instead of one per tensor), averaged and scattered back."""
-    eng = getattr(model, "_ddp_engine", None)
+    if isinstance(model, DistributedDataParallel):        # the wrapper itself (the natural call; FlatSGD accepts it too)
+        model.finish()
+        return
+    eng = getattr(model, "_ddp_engine", None)             # the wrapped inner module
     if eng is not None:
         eng.finish()
         return

@@ -186,16 +186,10 @@ class SymmWorld:
                 mem_handles.append(hr)
                 ptrs.append(C.symm_map(dev, hr, size, self.gran))
             if self.multicast:
-                try:
-                    mc_handle, mc_ptr = self._setup_multicast(h, size)
-                except Exception as e:  # host does not expose NVLS after all: degrade to two-shot
-                    self.nvls_error = repr(e)
+                # collective and failure-agreed: every rank gets a mapping or every rank degrades to two-shot together
+                mc_handle, mc_ptr = self._setup_multicast(h, size)
+                if not mc_ptr:
                     self.multicast = False
-                    mc_handle, mc_ptr = 0, 0
-                ok = [None] * self.world
-                dist.all_gather_object(ok, bool(mc_ptr), group=self.group)
-                if not all(ok):
-                    self.multicast, mc_ptr = False, 0
         else:
             p, hbytes = C.ipc_alloc(size)
             allh = [None] * self.world
@@ -209,21 +203,78 @@ class SymmWorld:
         self._handles.append(hd)
         return hd
 
+    def _agree(self, ok: bool) -> bool:
+        """Collective AND over the ranks of this world (every multicast set-up stage ends with one)."""
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        return all(flags)
+
     def _setup_multicast(self, mem_handle: int, size: int):
+        """Collective.  Binds this allocation to an NVSwitch multicast object; returns ``(mc_handle, mc_ptr)`` on every
+        rank, or ``(0, 0)`` on EVERY rank when any stage failed on any rank (``self.nvls_error`` says where).
+
+        Containers may report CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED without a fabric manager / IMEX behind it, so each
+        stage (create, fd exchange + import, add_device, bind, map) is followed by an agreement step: no rank is ever
+        left inside a collective the others skipped, and the fd-exchange tags advance on all ranks or on none."""
         C, dev = self.C, self.device.index
+        mc, fd, err = 0, -1, None
+        # ---- stage 1: rank 0 creates the object; everyone learns the outcome BEFORE any fd exchange is attempted
         if self.rank == 0:
-            mc, fd = C.mc_create(self.world, size)
-            self._exchange_fds(fd, only_from=0)
-            os.close(fd)
-        else:
-            got = self._exchange_fds(-1, only_from=0)
-            mc = C.symm_import(got[0])
-            os.close(got[0])
-        C.mc_add_device(mc, dev)
-        dist.barrier(group=self.group)
-        C.mc_bind(mc, mem_handle, size)
-        dist.barrier(group=self.group)
-        return mc, C.symm_map(dev, mc, size, self.gran)
+            try:
+                mc, fd = C.mc_create(self.world, size)
+            except Exception as e:
+                err = f"cuMulticastCreate: {e!r}"
+        created = [err is None if self.rank == 0 else None]
+        dist.broadcast_object_list(created, src=self.ranks[0], group=self.group)
+        if not created[0]:
+            self.nvls_error = err or "cuMulticastCreate failed on rank 0"
+            return 0, 0
+        # ---- stage 2: fd exchange (all ranks enter it: tags stay aligned) + import on the receivers
+        try:
+            if self.rank == 0:
+                self._exchange_fds(fd, only_from=0)
+            else:
+                got = self._exchange_fds(-1, only_from=0)
+                try:
+                    mc = C.symm_import(got[0])
+                finally:
+                    os.close(got[0])
+        except Exception as e:
+            err = f"multicast handle exchange/import: {e!r}"
+        finally:
+            if fd >= 0:
+                os.close(fd)
+        stage = "import"
+        mc_ptr = 0
+        ok = self._agree(err is None)
+        # ---- stages 3..5: add_device -> bind -> map, each agreed
+        for stage, fn in (("cuMulticastAddDevice", lambda: C.mc_add_device(mc, dev)),
+                          ("cuMulticastBindMem", lambda: C.mc_bind(mc, mem_handle, size)),
+                          ("map", lambda: C.symm_map(dev, mc, size, self.gran))):
+            if not ok:
+                break
+            res = None
+            try:
+                res = fn()
+            except Exception as e:
+                err = f"{stage}: {e!r}"
+            if stage == "map" and err is None:
+                mc_ptr = res
+            ok = self._agree(err is None)
+        if not ok:
+            self.nvls_error = err or f"multicast set-up failed on a peer rank (stage <= {stage})"
+            if mc_ptr:
+                try:
+                    C.symm_unmap(mc_ptr, size)
+                except Exception:
+                    pass
+            if mc:
+                try:
+                    C.symm_release(mc)
+                except Exception:
+                    pass
+            return 0, 0
+        return mc, mc_ptr
 
     def alloc(self, numel: int, dtype: torch.dtype) -> SymmHandle:
         """Collective: a symmetric buffer of ``numel`` elements (padded to 64) on every rank; ``handle.local`` is this

@@ -31,7 +31,7 @@ from .data import partition_dataset
 from .models.convnet import Net
 from .ops.optim import FlatSGD
 from .utils import say
-from .utils.checkpoint import load_checkpoint, save_checkpoint
+from .utils.checkpoint import load_checkpoint, restore_optimizer, save_checkpoint
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
 __all__ = ["run", "train", "TrainConfig"]
@@ -89,8 +89,8 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
         model._grad_bucket = GradBucket(list(model.parameters()))
         # optim.SGD(lr=0.01, momentum=0.5) of train_dist.py:110, over flat buffers: update + zero_grad in one pass
         optimizer = FlatSGD(model, lr=cfg.lr, momentum=cfg.momentum)
-        if cfg.resume and "optim" in resume_blob:
-            optimizer.load_state_dict(resume_blob["optim"])          # momentum buffers
+        if cfg.resume:
+            restore_optimizer(optimizer, model, resume_blob)         # momentum: FlatSGD layout or per-name (fused engine's)
         acc = torch.zeros((), device=device)
 
         # The native loader recycles its pinned staging buffers; the async H2D copies below must have left a buffer

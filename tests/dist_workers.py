@@ -180,7 +180,7 @@ def w_flat_sgd_ddp(rank, size):
         x, y = torch.randn(8 * size, 1, 28, 28, generator=g), torch.randint(0, 10, (8 * size,), generator=g)
         opt.zero_grad()
         F.nll_loss(ddp(x[rank * 8:(rank + 1) * 8]), y[rank * 8:(rank + 1) * 8]).backward()
-        b2.average_gradients(mine)
+        b2.average_gradients(ddp if it % 2 else mine)      # the wrapper and the wrapped module are both accepted
         opt.step()
         ref_opt.zero_grad()
         F.nll_loss(ref(x), y).backward()                   # mean over the global batch == mean of the per-rank means

@@ -76,3 +76,30 @@ def test_train_checkpoint_then_resume_accumulates_steps(tmp_path):
     torch.manual_seed(1234)
     assert not torch.equal(blob2["model"]["fc2.bias"], fresh.state_dict()["fc2.bias"])
     assert float(blob2["optim"]["momentum_buffers"][0].abs().sum()) > 0
+
+
+def test_named_momentum_roundtrip_across_layouts(tmp_path):
+    """The per-name momentum written next to FlatSGD's own state restores into a fresh optimizer (the form the fused
+    engine reads and writes), so checkpoints cross engines without losing momentum."""
+    import torch.nn.functional as F
+    from dist_tuto.pth_b200.utils.checkpoint import restore_optimizer
+    torch.manual_seed(3)
+    net = dist.Net().eval()
+    opt = dist.FlatSGD(net, lr=0.05, momentum=0.5)
+    x, y = torch.randn(8, 1, 28, 28), torch.randint(0, 10, (8,))
+    for _ in range(2):
+        opt.zero_grad()
+        F.nll_loss(net(x), y).backward()
+        opt.step()
+    path = str(tmp_path / "ck.pt")
+    dist.save_checkpoint(path, net, optimizer=opt, steps=2)
+    blob = torch.load(path)
+    assert set(blob["momentum"]) == {n for n, _ in net.named_parameters()}
+    assert float(blob["momentum"]["fc1.weight"].abs().max()) > 0
+    # a consumer that only understands the named form (what FusedTrainer.load_state_dict reads)
+    net2 = dist.Net().eval()
+    net2.load_state_dict(blob["model"])
+    opt2 = dist.FlatSGD(net2, lr=0.05, momentum=0.5)
+    restore_optimizer(opt2, net2, {"momentum": blob["momentum"]})
+    for a, b in zip(opt.momentum_flats, opt2.momentum_flats):
+        assert torch.equal(a, b)
