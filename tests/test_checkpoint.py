@@ -92,7 +92,7 @@ def test_named_momentum_roundtrip_across_layouts(tmp_path):
         F.nll_loss(net(x), y).backward()
         opt.step()
     path = str(tmp_path / "ck.pt")
-    dist.save_checkpoint(path, net, optimizer=opt, steps=2)
+    save_checkpoint(path, net, optimizer=opt, steps=2)
     blob = torch.load(path)
     assert set(blob["momentum"]) == {n for n, _ in net.named_parameters()}
     assert float(blob["momentum"]["fc1.weight"].abs().max()) > 0
