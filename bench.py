@@ -135,18 +135,24 @@ def ours(args):
             assert bsz2 == bsz
 
             # the call a user makes (train.py does exactly this per epoch): the C++ executor drives
-            # prefetch -> [H2D batch, convnet_step, allreduce_sgd, D2H loss] graph launches, one per step
-            done = 0
-            while done < W:
-                d, _ = tr.run_native(loader, max_steps=W - done)
-                done += d
+            # prefetch thread -> [H2D batch from the pinned ring, convnet_step, allreduce_sgd, D2H loss] per step.
+            # Warm-up and timed steps are consecutive steps of the SAME epoch (steady state of train()'s loop: the
+            # once-per-epoch index shuffle / prefetch-thread start is not inside a 20-step window, as it is not
+            # inside 468 of the 469 steps of an epoch); a new epoch starts only when the current one runs dry.
+            state = {"fresh": True}
+
+            def advance(n):
+                done = 0
+                while done < n:                          # an epoch has 60000/128 = 468 full batches
+                    d, fin = tr.run_native(loader, max_steps=n - done, new_epoch=state["fresh"])
+                    state["fresh"] = fin
+                    done += d
+
+            advance(W)
             b2.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            done = 0
-            while done < K:                              # an epoch has 60000/128 = 468 full batches
-                d, _ = tr.run_native(loader, max_steps=K - done)
-                done += d
+            advance(K)
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
             ex = tr._executors[id(loader)][0]
             exec_chunk = int(os.environ.get("B200DIST_EXEC_CHUNK", "1")) if ex.chunking() else 1

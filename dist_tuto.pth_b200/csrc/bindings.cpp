@@ -64,6 +64,23 @@ int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias
                         int out_bf16, cudaStream_t stream);
 const char* b2_gemm_last_error();
 int b2_gemm_probe_m64(const void* a, const void* b, float* dump, cudaStream_t stream);
+struct BtBuffers {
+  void *P1, *P2, *H, *DH, *dP2, *DC, *W2K, *W2R, *W3K, *W3T;
+  unsigned char *A1, *A2;
+  float *Hrelu, *DLOG, *G1, *B3P;
+};
+const char* b2_bt_last_error();
+int b2_bt_pack_weights(const float* params, const BtBuffers* bf, cudaStream_t stream);
+int b2_bt_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target, const BtBuffers* bf,
+                      float* loss_acc, float* out_logp, const unsigned long long* step, unsigned long long seed,
+                      long long sample_base, int B, int training, int backward, float inv_bsz, float p_drop, int stage_mask,
+                      cudaStream_t stream);
+const char* b2_probe_last_error();
+int b2_tma_probe(const void* tensor, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                 const unsigned int* box, int swizzle, const int* coords, unsigned int bytes, unsigned char* out,
+                 cudaStream_t stream);
+int b2_umma_probe(const unsigned char* a_img, unsigned int a_bytes, const unsigned char* b_img, unsigned int b_bytes,
+                  unsigned int idesc, const unsigned long long* ops, int n_ops, int ncols, float* dump, cudaStream_t stream);
 }
 
 namespace {
@@ -337,6 +354,88 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (rc != 0) throw std::runtime_error(std::string("gemm_probe_m64: ") + b2_gemm_last_error());
     return dump;
   });
+
+  // ------------------------------------------------------------------ batched tensor-core engine (csrc/convnet_batched.cu)
+  // bufs: [P1, P2, H, DH, dP2, DC, W2K, W2R, W3K, W3T, A1, A2, Hrelu, DLOG, G1, B3P] (see ops/convnet_batched.py)
+  auto bt_bufs = [](const std::vector<torch::Tensor>& v, int64_t B) {
+    TORCH_CHECK(v.size() == 16, "bufs: 16 tensors");
+    const int64_t need[16] = {B * 3072, B * 320, B * 64, B * 64, B * 320, B * 2048, 32 * 448, 400 * 64, 64 * 320, 320 * 64,
+                              B * 1440, B * 320, B * 64, B * 16, B * 1440, 64};
+    for (int i = 0; i < 16; ++i) {
+      TORCH_CHECK(v[i].is_cuda() && v[i].is_contiguous() && v[i].numel() >= need[i], "bufs[", i, "] too small / not CUDA");
+      const auto want = i < 10 ? torch::kBFloat16 : (i < 12 ? torch::kUInt8 : torch::kFloat32);
+      TORCH_CHECK(v[i].scalar_type() == want, "bufs[", i, "] dtype");
+      TORCH_CHECK(((uintptr_t)v[i].data_ptr() & 127) == 0, "bufs[", i, "] must be 128-byte aligned");
+    }
+    BtBuffers b;
+    b.P1 = v[0].data_ptr(); b.P2 = v[1].data_ptr(); b.H = v[2].data_ptr(); b.DH = v[3].data_ptr(); b.dP2 = v[4].data_ptr();
+    b.DC = v[5].data_ptr(); b.W2K = v[6].data_ptr(); b.W2R = v[7].data_ptr(); b.W3K = v[8].data_ptr(); b.W3T = v[9].data_ptr();
+    b.A1 = v[10].data_ptr<uint8_t>(); b.A2 = v[11].data_ptr<uint8_t>();
+    b.Hrelu = v[12].data_ptr<float>(); b.DLOG = v[13].data_ptr<float>(); b.G1 = v[14].data_ptr<float>(); b.B3P = v[15].data_ptr<float>();
+    return b;
+  };
+  m.def("bt_pack_weights", [bt_bufs](torch::Tensor params, std::vector<torch::Tensor> bufs) {
+    check_cuda_contig(params, "params");
+    TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar());
+    BtBuffers b = bt_bufs(bufs, 0);
+    c10::cuda::CUDAGuard guard(params.device());
+    ck_cuda(b2_bt_pack_weights(params.data_ptr<float>(), &b, cur_stream()), "bt_pack_weights launch");
+  });
+  m.def("bt_step", [bt_bufs](torch::Tensor params, c10::optional<torch::Tensor> grads, torch::Tensor x, torch::Tensor target,
+                             std::vector<torch::Tensor> bufs, c10::optional<torch::Tensor> loss_acc,
+                             c10::optional<torch::Tensor> out_logp, c10::optional<torch::Tensor> step, uint64_t seed,
+                             int64_t sample_base, bool training, double inv_bsz, double p_drop, int stage_mask) {
+    check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
+    TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
+    TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
+    const bool u8 = x.scalar_type() == torch::kUInt8;
+    TORCH_CHECK(u8 || x.scalar_type() == torch::kFloat32, "x: float32 (normalised) or uint8 (raw)");
+    const int B = (int)target.numel();
+    TORCH_CHECK(x.numel() == (int64_t)B * 784, "x must be [B,1,28,28]");
+    float* g = nullptr;
+    if (grads.has_value()) { check_cuda_contig(*grads, "grads"); TORCH_CHECK(grads->scalar_type() == torch::kFloat32 && grads->numel() >= b2_convnet_npar()); g = grads->data_ptr<float>(); }
+    float* la = loss_acc.has_value() ? loss_acc->data_ptr<float>() : nullptr;
+    float* lp = nullptr;
+    if (out_logp.has_value()) { TORCH_CHECK(out_logp->numel() == (int64_t)B * 10 && out_logp->scalar_type() == torch::kFloat32); lp = out_logp->data_ptr<float>(); }
+    const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
+    BtBuffers b = bt_bufs(bufs, B);
+    c10::cuda::CUDAGuard guard(params.device());
+    int rc = b2_bt_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
+                               &b, la, lp, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
+                               stage_mask, cur_stream());
+    if (rc != 0) throw std::runtime_error(std::string("bt_step: ") + b2_bt_last_error());
+  }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("bufs"), py::arg("loss_acc"),
+     py::arg("out_logp"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
+     py::arg("p_drop") = 0.5, py::arg("stage_mask") = 255);
+
+  // ------------------------------------------------------------------ tensor-core layout probes (tests/test_gpu_tc_probe.py)
+  m.def("tma_probe", [](torch::Tensor tensor, std::vector<unsigned long long> dims, std::vector<unsigned long long> strides_bytes,
+                        std::vector<unsigned int> box, int swizzle, std::vector<int> coords) {
+    // one TMA box load of a uint16 tensor map -> the raw shared-memory image (uint8)
+    check_cuda_contig(tensor, "tensor");
+    const int rank = (int)dims.size();
+    TORCH_CHECK(rank >= 2 && rank <= 5 && (int)box.size() == rank && (int)coords.size() == rank && (int)strides_bytes.size() == rank - 1);
+    size_t bytes = 2;
+    for (auto b : box) bytes *= b;
+    coords.resize(5, 0);
+    auto out = torch::zeros({(int64_t)bytes}, tensor.options().dtype(torch::kUInt8));
+    c10::cuda::CUDAGuard guard(tensor.device());
+    int rc = b2_tma_probe(tensor.data_ptr(), rank, dims.data(), strides_bytes.data(), box.data(), swizzle, coords.data(),
+                          (unsigned int)bytes, out.data_ptr<uint8_t>(), cur_stream());
+    if (rc != 0) throw std::runtime_error(std::string("tma_probe: ") + b2_probe_last_error());
+    return out;
+  }, py::arg("tensor"), py::arg("dims"), py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle"), py::arg("coords"));
+  m.def("umma_probe", [](torch::Tensor a_img, torch::Tensor b_img, unsigned int idesc, std::vector<unsigned long long> ops, int ncols) {
+    // ops: flat list of (adesc, bdesc, tmem_col, accumulate) quadruples; returns TMEM[128 lanes, ncols] fp32
+    check_cuda_contig(a_img, "a_img"); check_cuda_contig(b_img, "b_img");
+    TORCH_CHECK(a_img.scalar_type() == torch::kUInt8 && b_img.scalar_type() == torch::kUInt8 && ops.size() % 4 == 0);
+    auto dump = torch::zeros({128, ncols}, a_img.options().dtype(torch::kFloat32));
+    c10::cuda::CUDAGuard guard(a_img.device());
+    int rc = b2_umma_probe(a_img.data_ptr<uint8_t>(), (unsigned int)a_img.numel(), b_img.data_ptr<uint8_t>(), (unsigned int)b_img.numel(),
+                           idesc, ops.data(), (int)(ops.size() / 4), ncols, dump.data_ptr<float>(), cur_stream());
+    if (rc != 0) throw std::runtime_error(std::string("umma_probe: ") + b2_probe_last_error());
+    return dump;
+  }, py::arg("a_img"), py::arg("b_img"), py::arg("idesc"), py::arg("ops"), py::arg("ncols"));
 
   // ------------------------------------------------------------------ native step executor
   py::class_<ExecutorPy>(m, "StepExecutor")
