@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--ref-avg", default="tutorial", choices=["tutorial", "committed"])
     ap.add_argument("--graph-chunk", type=int, default=50)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--loader-buffers", type=int, default=6, help="pinned ring depth of the native loader (e2e arm)")
+    ap.add_argument("--loader-buffers", type=int, default=24, help="pinned ring depth of the native loader (e2e arm)")
     return ap.parse_args()
 
 
@@ -155,7 +155,7 @@ def ours(args):
             advance(K)
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
             ex = tr._executors[id(loader)][0]
-            exec_chunk = int(os.environ.get("B200DIST_EXEC_CHUNK", "1")) if ex.chunking() else 1
+            exec_chunk = getattr(tr, "exec_chunk", 1) if ex.chunking() else 1
             torch.cuda.synchronize()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
             e2e = bsz * size * K / (e2e_ms / 1e3)
@@ -175,7 +175,8 @@ def ours(args):
                                             "graph_chunk": G, "symm": sym,
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
                                                         "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "
-                                                        + (f"{exec_chunk} steps per cudaGraphLaunch" if exec_chunk > 1 else "one cudaGraphLaunch per step")}),
+                                                        + (f"chunks of {exec_chunk} steps = 3 graph launches on 3 streams ({exec_chunk} H2D nodes | {2 * exec_chunk} kernels | {exec_chunk} D2H nodes)"
+                                                           if exec_chunk > 1 else "one cudaGraphLaunch per step")}),
                   flush=True)
 
     rank = int(os.environ.get("RANK", 0))

@@ -5,7 +5,7 @@ Public surface (tutorial names kept; see each module for file:line parity):
 
     init_processes / launch / init_from_env            launch.py
     send recv isend irecv                               comm.py
-    all_reduce reduce broadcast scatter gather all_gather barrier new_group
+    all_reduce reduce broadcast scatter gather gather_to_root all_gather barrier new_group
     reduce_op get_rank get_world_size                   comm.py
     allreduce (ring) / allreduce_chunked                ring.py
     Partition DataPartitioner partition_dataset         data.py
@@ -15,7 +15,7 @@ Public surface (tutorial names kept; see each module for file:line parity):
     run / train / TrainConfig                           train.py
 """
 from .comm import (reduce_op, ReduceOp, send, recv, isend, irecv, broadcast, reduce, all_reduce,  # noqa: F401
-                   scatter, gather, all_gather, barrier, new_group, get_rank, get_world_size,
+                   scatter, gather, gather_to_root, all_gather, barrier, new_group, get_rank, get_world_size,
                    is_initialized, group)
 from .launch import (init_processes, init_process, launch, init_from_env, shutdown, find_free_port,  # noqa: F401
                      LaunchError)

@@ -28,7 +28,7 @@ import torch.distributed as dist
 
 __all__ = [
     "reduce_op", "ReduceOp", "send", "recv", "isend", "irecv", "broadcast", "reduce",
-    "all_reduce", "scatter", "gather", "all_gather", "barrier", "new_group",
+    "all_reduce", "scatter", "gather", "gather_to_root", "all_gather", "barrier", "new_group",
     "get_rank", "get_world_size", "is_initialized", "Request", "group_ranks",
 ]
 
@@ -216,6 +216,19 @@ def gather(tensor: torch.Tensor, dst: int = 0, gather_list: Optional[List[torch.
     elif gather_list is not None and len({id(t) for t in gather_list}) != len(gather_list):
         raise ValueError("gather_list must hold distinct tensors ([zeros(1)] * n aliases one buffer)")
     return dist.gather(tensor, gather_list=gather_list, dst=dst, group=g)
+
+
+def gather_to_root(tensor: torch.Tensor, rank: int, tensor_list: Optional[List[torch.Tensor]] = None, root: int = 0,
+                   group=None):
+    """The ``gather(tensor, rank, tensor_list=None, root=0, group=None)`` helper of ptp.py:9-19, same argument order.
+
+    "Sends tensor to root process, which store it in tensor_list."  The 2017 internals it called
+    (``dist.gather_recv`` / ``dist.gather_send``, ptp.py:17,19) no longer exist; both map onto one ``gather`` collective
+    here.  The root must pass ``tensor_list`` (the reference asserts the same, ptp.py:16)."""
+    if rank == root:
+        assert tensor_list is not None, "the root rank must provide tensor_list"
+        return gather(tensor, dst=root, gather_list=tensor_list, group=group)
+    return gather(tensor, dst=root, gather_list=None, group=group)
 
 
 def all_gather(tensor_list: List[torch.Tensor], tensor: torch.Tensor, group=None):

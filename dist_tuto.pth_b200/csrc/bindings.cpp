@@ -43,7 +43,7 @@ int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, cudaStream_t stream);
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -161,15 +161,18 @@ struct ExecutorPy {
              std::vector<unsigned long long> grad_ptrs, std::vector<unsigned long long> sig_ptrs, torch::Tensor step,
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
-             int max_in_flight, int cluster, torch::Tensor aux, int chunk, std::vector<unsigned long long> inbox)
-      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux} {
+             int max_in_flight, int cluster, torch::Tensor aux, int chunk, std::vector<unsigned long long> inbox,
+             torch::Tensor loss_hist)
+      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux, loss_hist} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
     const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
     chunk = std::max(1, std::min(chunk, 8));
-    const size_t nblk = (size_t)std::max(2, chunk);
+    const size_t nblk = (size_t)std::max(2, 2 * chunk);
     TORCH_CHECK(in_dev.is_cuda() && in_dev.scalar_type() == torch::kUInt8 && (size_t)in_dev.numel() >= nblk * block,
-                "in_dev: CUDA uint8 buffer of >= max(2, chunk) * block bytes");
+                "in_dev: CUDA uint8 buffer of >= max(2, 2 * chunk) * block bytes");
+    TORCH_CHECK(loss_hist.is_cuda() && loss_hist.scalar_type() == torch::kFloat32 && loss_hist.numel() >= 4 * chunk,
+                "loss_hist: CUDA fp32 [2 * chunk, 2]");
     b2::StepConfig c;
     std::memset(&c, 0, sizeof(c));
     c.params = params.data_ptr<float>(); c.momentum = momentum.data_ptr<float>(); c.grads_local = grads.data_ptr<float>();
@@ -179,6 +182,7 @@ struct ExecutorPy {
     c.done_counter = reinterpret_cast<unsigned int*>(done_counter.data_ptr());
     c.loss_acc = loss_acc.data_ptr<float>();
     for (size_t i = 0; i < nblk; ++i) c.in_dev[i] = in_dev.data_ptr<uint8_t>() + i * block;
+    c.loss_hist = loss_hist.data_ptr<float>();
     c.chunk = chunk;
     c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
     c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;
@@ -272,7 +276,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
                                     (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax,
-                                    inbox.empty() ? nullptr : &ib, cur_stream()),
+                                    inbox.empty() ? nullptr : &ib, nullptr, nullptr, cur_stream()),
             "allreduce_sgd launch");
   }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
      py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
@@ -442,13 +446,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
                     int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int,
-                    std::vector<unsigned long long>>(),
+                    std::vector<unsigned long long>, torch::Tensor>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
            py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::arg("chunk") = 1,
-           py::arg("inbox") = std::vector<unsigned long long>(), py::keep_alive<1, 2>())
+           py::arg("inbox") = std::vector<unsigned long long>(), py::arg("loss_hist") = torch::Tensor(), py::keep_alive<1, 2>())
       .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
       .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)

@@ -20,9 +20,10 @@ struct StepConfig {
   unsigned long long* step_counter;
   unsigned int* done_counter;
   float* loss_acc;                   // [2]
-  unsigned char* in_dev[8];          // device input blocks, same layout as a loader slot: [x | pad | y]; [0..1] double-buffer
-                                     // the per-step path, [0..chunk) are the blocks of a chunk graph
-  int chunk;                         // steps per chunk graph (0/1 = per-step launches only), <= 8
+  unsigned char* in_dev[16];         // device input blocks, same layout as a loader slot: [x | pad | y]; [0..1] double-buffer
+                                     // the per-step path, [g*chunk .. g*chunk+chunk) are the blocks of chunk group g (0/1)
+  float* loss_hist;                  // device [2*chunk][2]: cumulative loss as of each step of a chunk (written by the SGD kernel)
+  int chunk;                         // steps per chunk (0/1 = per-step launches only), <= 8
   int B, x_u8, training, rank, world, cluster;
   unsigned long long seed;
   long long sample_base, grad_stride;
@@ -52,8 +53,8 @@ class StepExecutor {
     float* loss_pin = nullptr;
   };
   bool capture(int parity);
-  bool capture_chunk(int group);
-  void record_step(const void* x, const long long* y);
+  bool capture_chunk(int slot_group, int g);
+  void record_step(const void* x, const long long* y, float* loss_snapshot = nullptr);
   void retire_oldest();
   StepConfig cfg_;
   NativeLoader* loader_;
@@ -62,10 +63,12 @@ class StepExecutor {
   cudaGraphExec_t exec_[2] = {nullptr, nullptr};     // the two kernels, reading in_dev[parity]
   cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr};
   std::vector<Slot> slots_;
-  // chunk graphs: K consecutive steps (K H2D copies, 2K kernels, K loss read-backs) as ONE graph launch; one graph per
-  // group of K loader slots (the slot of batch b is b % num_slots, so the pinned addresses of a group are fixed)
-  std::vector<cudaGraphExec_t> chunk_exec_;
-  std::vector<cudaEvent_t> chunk_ev_;  // capture-time fork/join events
+  // chunk pipeline: K consecutive steps = three graph launches on three streams (see executor.cpp).  The slot of batch b is
+  // b % num_slots, so the pinned addresses of a slot group are fixed; g = chunk parity selects the device block group.
+  std::vector<cudaGraphExec_t> h2d_exec_, d2h_exec_;   // [slot_group * 2 + g]
+  cudaGraphExec_t comp_exec_[2] = {nullptr, nullptr};
+  cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, comp_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
+  int64_t chunks_issued_ = 0;
   bool chunk_ok_ = false;
   struct Flight { int slot, ev_slot; };
   std::deque<Flight> in_flight_;

@@ -32,7 +32,16 @@ struct SgdArgs {
   long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
   float* aux;                // optional [w2f 5000 | w2b 8000]: conv2.weight re-arranged for the forward/backward kernels
   PeerPtrs inbox;            // push variant only: every rank's inbox  [2 parities][world sources][n_vec][2 lines of 16 B]
+  const float* loss_acc;     // optional: the step kernels' running [sum of batch-mean nll, #correct] ...
+  float* loss_snapshot;      // ... copied here (2 floats) = the cumulative loss as of THIS step (per-step D2H source)
 };
+
+// The previous kernel of the stream (this step's forward/backward) is complete and the next step's kernel cannot pass its
+// own griddepcontrol.wait before this kernel ends, so loss_acc holds exactly the loss up to and including this step.
+__device__ __forceinline__ void snapshot_loss(const SgdArgs& a) {
+  if (a.loss_snapshot != nullptr && blockIdx.x == 0 && threadIdx.x < 2)
+    a.loss_snapshot[threadIdx.x] = *reinterpret_cast<const volatile float*>(a.loss_acc + threadIdx.x);
+}
 
 // SGD update of one float4 vector (+ the pre-arranged conv2.weight copies), shared by both exchange variants
 __device__ __forceinline__ void sgd_apply(const SgdArgs& a, size_t v, float4 g) {
@@ -63,6 +72,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   __shared__ unsigned int s_par;
   pdl_wait();                        // gradients of this step (previous kernel) are complete and visible
   pdl_launch_dependents();           // the next step's forward/backward kernel may pre-launch now (it zeroes its smem, then waits)
+  snapshot_loss(a);
   unsigned long long st = 0ull;
   unsigned int seen = 0u;
   if (threadIdx.x == 0) {
@@ -130,6 +140,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs
   __shared__ unsigned long long s_step;
   pdl_wait();
   pdl_launch_dependents();
+  snapshot_loss(a);
   unsigned int seen = 0u;
   if (threadIdx.x == 0) {
     s_step = *reinterpret_cast<volatile unsigned long long*>(a.step);
@@ -224,8 +235,9 @@ extern "C" {
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, cudaStream_t stream) {
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, cudaStream_t stream) {
   b2::SgdArgs a;
+  a.loss_acc = loss_acc; a.loss_snapshot = (loss_acc != nullptr) ? loss_snapshot : nullptr;
   memset(&a.inbox, 0, sizeof(a.inbox));
   // push ("LL") exchange: needs an inbox on every rank, the double-buffered buckets and the device step counter (its epoch)
   const bool push = inbox != nullptr && world > 1;

@@ -289,7 +289,7 @@ class NativeBatchLoader:
 
     def __init__(self, partition, batch_size: int, shuffle: bool = True, drop_last: bool = False,
                  pin_memory: Optional[bool] = None, seed: Optional[int] = None, raw_uint8: bool = False,
-                 num_buffers: int = 6):
+                 num_buffers: int = 24):
         from .ops import _ext
         base = partition.data if isinstance(partition, Partition) else partition
         if not hasattr(base, "images"):

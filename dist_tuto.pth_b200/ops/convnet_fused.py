@@ -327,18 +327,22 @@ class FusedTrainer:
             if loader.batch_size != self.bsz:
                 raise ValueError("loader batch size != trainer batch size")
             block = (int(loader._l.block_bytes()) + 255) // 256 * 256
-            # B200DIST_EXEC_CHUNK=K: K steps per graph launch when the loader ring allows it (num_buffers % K == 0, >= 2K),
-            # see executor.cpp.  Off by default: measured on B200 (profiles/executor_chunk_graphs.json) the per-step
-            # H2D -> kernel edge keeps the programmatic-dependent-launch overlap from forming inside the chunk, so a
-            # chunk costs as much per step as single-step graphs plus a ~20 us bubble between chunks.
-            chunk = max(1, min(8, int(os.environ.get("B200DIST_EXEC_CHUNK", "1"))))
-            in_dev = torch.zeros(max(2, chunk) * block, dtype=torch.uint8, device=self.device)
+            # chunk pipeline (csrc/executor.cpp): K steps = 3 graph launches (K H2D nodes | 2K kernels | K D2H nodes) on
+            # three streams.  K = a third of the loader ring (<= 8); B200DIST_EXEC_CHUNK overrides (1 = per-step launches).
+            env = os.environ.get("B200DIST_EXEC_CHUNK")
+            chunk = int(env) if env is not None else loader.num_buffers // 3
+            chunk = max(1, min(8, chunk))
+            while chunk > 1 and (loader.num_buffers % chunk != 0 or loader.num_buffers < 3 * chunk):
+                chunk -= 1
+            in_dev = torch.zeros(max(2, 2 * chunk) * block, dtype=torch.uint8, device=self.device)
+            loss_hist = torch.zeros(4 * max(1, chunk), dtype=torch.float32, device=self.device)
             ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
-                                      self.cluster, self.aux, chunk, self._inbox_ptrs),
+                                      self.cluster, self.aux, chunk, self._inbox_ptrs, loss_hist),
                   self.training)
+            self.exec_chunk = chunk
             self._executors[id(loader)] = ex
         if new_epoch:
             loader.begin_epoch()

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["sw128_offset", "image_rows128", "smem_desc", "idesc_bf16", "expected_tma_image", "bf16_bits", "bits_to_f32"]
+__all__ = ["sw128_offset", "sw32_offset", "image_rows128", "image_rows32", "expected_tma_image_sw32", "smem_desc", "idesc_bf16", "expected_tma_image", "bf16_bits", "bits_to_f32"]
 
 
 def sw128_offset(row: int, byte_in_row: int, sbo: int = 1024) -> int:
@@ -49,6 +49,37 @@ def image_rows128(mat_bits: np.ndarray, sbo: int = 1024) -> np.ndarray:
         for c in range(8):
             o = sw128_offset(r, c * 16, sbo)
             img[o:o + 16] = raw[r, c * 16:(c + 1) * 16]
+    return img
+
+
+def sw32_offset(row: int, byte_in_row: int) -> int:
+    """Byte offset inside a 32B-swizzled tile of 32-byte rows (Swizzle<1,4,3>: address bit 4 ^= address bit 7)."""
+    o = row * 32 + byte_in_row
+    return o ^ (((o >> 7) & 1) << 4)
+
+
+def image_rows32(mat_bits: np.ndarray) -> np.ndarray:
+    """uint16 matrix [rows, 16] -> uint8 image of a 32B-swizzled tile: the K-major image of ``mat`` (rows = M/N index, 16 K
+    elements per row) and the MN-major image of its transpose (rows = K index, 16 consecutive MN elements per row)."""
+    rows = mat_bits.shape[0]
+    assert mat_bits.shape[1] == 16 and mat_bits.dtype == np.uint16 and rows % 8 == 0
+    img = np.zeros(rows * 32, dtype=np.uint8)
+    raw = mat_bits.view(np.uint8).reshape(rows, 32)
+    for r in range(rows):
+        for c in range(2):
+            o = sw32_offset(r, c * 16)
+            img[o:o + 16] = raw[r, c * 16:(c + 1) * 16]
+    return img
+
+
+def expected_tma_image_sw32(box_vals: np.ndarray) -> np.ndarray:
+    """SWIZZLE_32B counterpart of :func:`expected_tma_image` (address bit 4 ^= address bit 7 of the dense byte stream)."""
+    raw = np.ascontiguousarray(box_vals).view(np.uint8).reshape(-1)
+    assert raw.size % 256 == 0
+    img = np.zeros(raw.size, dtype=np.uint8)
+    for o in range(0, raw.size, 16):
+        d = o ^ (((o >> 7) & 1) << 4)
+        img[d:d + 16] = raw[o:o + 16]
     return img
 
 

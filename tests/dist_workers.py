@@ -64,6 +64,11 @@ def w_collectives(rank, size):
     b2.gather(torch.ones(1), dst=0, gather_list=tl, group=0)
     s = sum(tl)[0]
     assert s == (size if rank == 0 else 0)
+    # the ptp.py:9-19 helper: gather(tensor, rank, tensor_list, root, group), non-zero root
+    tl2 = [torch.zeros(1) for _ in range(size)]
+    b2.gather_to_root(torch.full((1,), float(rank + 1)), rank, tl2 if rank == size - 1 else None, root=size - 1)
+    if rank == size - 1:
+        assert [float(t) for t in tl2] == [float(r + 1) for r in range(size)]
     # all_gather
     tl = [torch.zeros(1) for _ in range(size)]
     b2.all_gather(tl, torch.full((1,), float(rank)))
