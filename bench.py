@@ -36,8 +36,56 @@ def parse():
     ap.add_argument("--ref-avg", default="tutorial", choices=["tutorial", "committed"])
     ap.add_argument("--graph-chunk", type=int, default=50)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--large-batch", type=int, default=4096,
+                    help="per-GPU batch of the extra large-batch (throughput, weak-scaling) measurement; 0 = skip")
     ap.add_argument("--loader-buffers", type=int, default=24, help="pinned ring depth of the native loader (e2e arm)")
     return ap.parse_args()
+
+
+def large_batch_arm(torch, b2, LB, rank, size, dev, max_over_ranks, steps=12):
+    """Device-timed samples/s of full training steps at per-GPU batch ``LB`` (weak scaling) on the batched tcgen05 engine."""
+    from dist_tuto.pth_b200.ops.convnet_batched import BatchedTrainer
+    tr = BatchedTrainer(LB, lr=0.01, momentum=0.5, seed=1234, device=dev, p_drop=0.5, raw_uint8=True)
+    npool = steps + 1
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    xs = torch.randint(0, 256, (npool, LB, 1, 28, 28), dtype=torch.uint8, device=dev, generator=g)
+    ys = torch.randint(0, 10, (npool, LB), device=dev, generator=g)
+    st = tr.stream
+    with torch.cuda.stream(st):
+        for i in range(3):
+            tr._kernels(xs[i], ys[i], LB)
+    st.synchronize()
+    graphs = []
+    for i in range(npool):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            tr._kernels(xs[i], ys[i], LB)
+        graphs.append(gr)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(st):
+        for gr in graphs:
+            gr.replay()
+    st.synchronize()
+    b2.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        flush.fill_(1)
+        graphs[0].replay()                      # pre-roll (untimed): ranks aligned by its exchange
+        e0.record(st)
+        for i in range(1, npool):
+            graphs[i].replay()
+        e1.record(st)
+    st.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    loss = float(tr.loss_acc[0].item())
+    out = {"per_gpu_batch": LB, "global_batch": LB * size, "scaling": "weak", "steps": steps, "us_per_step": ms / steps * 1e3,
+           "samples_per_s": LB * size * steps / (ms / 1e3), "dtype": "bf16 tensor-core operands (tcgen05), fp32 accumulate / master weights",
+           "engine": "batched: conv2 fwd/dgrad/wgrad + fc1 on tcgen05 with TMA-fed operands, fused all-reduce+SGD kernel",
+           "launches_per_step": tr.gpu_launches_per_step, "loss_finite": loss == loss,
+           "l2": "L2 flushed before the pre-roll; every timed step reads a batch not touched since"}
+    del graphs, tr
+    return out
 
 
 def ours(args):
@@ -151,20 +199,32 @@ def ours(args):
             advance(W)
             b2.barrier()
             torch.cuda.synchronize()
+            tr._executors[id(loader)][0].reset_stats()
             t0 = time.perf_counter()
             advance(K)
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
             ex = tr._executors[id(loader)][0]
+            host_stats = {k: (round(v, 1) if isinstance(v, float) else v) for k, v in ex.stats().items()}
             exec_chunk = getattr(tr, "exec_chunk", 1) if ex.chunking() else 1
             torch.cuda.synchronize()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
             e2e = bsz * size * K / (e2e_ms / 1e3)
             assert seen == seen
+        # ------------------------------------------------------------ extra key: BASELINE.md B1 "large-batch variant"
+        # Same network / optimizer / data-parallel exchange at a throughput-sized per-GPU batch (weak scaling), run by the
+        # batched tensor-core engine (csrc/convnet_batched.cu).  Not the headline: `value` above stays global batch 128.
+        large = None
+        if args.large_batch > 0:
+            try:
+                large = large_batch_arm(torch, b2, args.large_batch, rank, size, dev, max_over_ranks)
+            except Exception as e:      # never take the headline down
+                large = {"error": f"{type(e).__name__}: {e}"[:300]}
         if rank == 0:
             sym = tr.symm.describe() if tr.symm is not None else {"world": 1}
             print(result_line(impl="ours", value=value, ms=ms, n_gpus=size, steps=K, warmup=W, clocks=clocks,
-                              e2e_value=e2e, h2d=h2d, d2h=8, gpu_launches=2 * K, dtype="fp32",
-                              extra_config={"engine": "fused convnet_step (cluster-per-sample for small per-GPU batches) + allreduce_sgd kernels, CUDA graph, PDL",
+                              e2e_value=e2e, h2d=h2d, d2h=8, gpu_launches=tr.gpu_launches_per_step * K, dtype="fp32",
+                              extra_config={"engine": ("ONE kernel per step: fused convnet_step (cluster-per-sample for small per-GPU batches) whose tail does the gradient exchange + SGD; CUDA graph, PDL"
+                                                       if tr.fused_tail else "fused convnet_step (cluster-per-sample for small per-GPU batches) + allreduce_sgd kernels, CUDA graph, PDL"),
                                             "precision": "fp32 SIMT forward/backward (>= the required bf16); fp32 gradients on the wire; fp32 SGD",
                                             "cluster_ctas_per_sample": tr.cluster,
                                             "gradient_exchange": ("push: flag-in-data stores into peer inboxes, local reduce" if tr.inbox_handle is not None
@@ -176,7 +236,9 @@ def ours(args):
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
                                                         "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "
                                                         + (f"chunks of {exec_chunk} steps = 3 graph launches on 3 streams ({exec_chunk} H2D nodes | {2 * exec_chunk} kernels | {exec_chunk} D2H nodes)"
-                                                           if exec_chunk > 1 else "one cudaGraphLaunch per step")}),
+                                                           if exec_chunk > 1 else "one cudaGraphLaunch per step"),
+                                            "e2e_host_us": host_stats if not args.no_e2e else None,
+                                            "large_batch": large}),
                   flush=True)
 
     rank = int(os.environ.get("RANK", 0))

@@ -26,7 +26,7 @@ TARGET = os.path.join(HERE, "_C.so")
 
 CU_SOURCES = ["allreduce.cu", "convnet.cu", "convnet_cluster.cu", "sgd.cu", "gemm_tcgen05.cu", "tc_probe.cu", "convnet_batched.cu"]
 CPP_SOURCES = ["symm_mem.cpp", "loader.cpp", "executor.cpp", "bindings.cpp"]
-HEADERS = ["common.cuh", "tc_common.cuh", "convnet_args.cuh", "loader.h", "executor.h"]
+HEADERS = ["common.cuh", "tc_common.cuh", "convnet_args.cuh", "sgd_device.cuh", "loader.h", "executor.h"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

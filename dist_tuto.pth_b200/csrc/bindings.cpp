@@ -51,12 +51,13 @@ int b2_convnet_npar();
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream);
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
+                           const void* tail, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, cudaStream_t stream);
+                              const float* aux, const void* tail, cudaStream_t stream);
 void b2_convnet_set_tc(int on);
 int b2_convnet_get_tc();
 int b2_gemm_available();
@@ -64,6 +65,19 @@ int b2_gemm_bf16_launch(const void* a, const void* b, void* c, const float* bias
                         int out_bf16, cudaStream_t stream);
 const char* b2_gemm_last_error();
 int b2_gemm_probe_m64(const void* a, const void* b, float* dump, cudaStream_t stream);
+struct FusedTailHost {            // mirrors cn::FusedTailHost (csrc/convnet_args.cuh)
+  void* grad_ptrs[8];
+  void* inbox_ptrs[8];
+  float* params;
+  float* momentum;
+  unsigned long long* step;
+  float* aux;
+  const float* loss_acc;
+  float* loss_snapshot;
+  unsigned int* ticket;
+  float lr, mu, scale;
+  int rank, world;
+};
 struct BtBuffers {
   void *P1, *P2, *H, *DH, *dP2, *DC, *W2K, *W2R, *W3K, *W3T;
   unsigned char *A1, *A2;
@@ -162,8 +176,8 @@ struct ExecutorPy {
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
              int max_in_flight, int cluster, torch::Tensor aux, int chunk, std::vector<unsigned long long> inbox,
-             torch::Tensor loss_hist)
-      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux, loss_hist} {
+             torch::Tensor loss_hist, bool fused_tail, torch::Tensor ticket)
+      : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux, loss_hist, ticket} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
     const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
@@ -192,9 +206,16 @@ struct ExecutorPy {
     TORCH_CHECK(inbox.empty() || (int)inbox.size() == world, "inbox: one pointer per rank (or none)");
     for (size_t i = 0; i < inbox.size() && i < 8; ++i) c.inbox_ptrs[i] = (void*)(uintptr_t)inbox[i];
     c.push = !inbox.empty();
+    c.fused_tail = fused_tail ? 1 : 0;
+    if (fused_tail) {
+      TORCH_CHECK(ticket.is_cuda() && ticket.scalar_type() == torch::kInt32 && ticket.numel() >= 2, "ticket: CUDA int32 [2]");
+      TORCH_CHECK(world == 1 || c.push, "the fused tail needs the push inbox when world > 1");
+      c.ticket = reinterpret_cast<unsigned int*>(ticket.data_ptr());
+    }
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
     impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
+    if (!impl->prepare()) throw std::runtime_error("StepExecutor: " + impl->error());
   }
   py::tuple run(int64_t max_steps) {
     int pending = -1, epoch_done = 0;
@@ -299,7 +320,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                            c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
                            c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
                            int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride, int cluster,
-                           c10::optional<torch::Tensor> aux) {
+                           c10::optional<torch::Tensor> aux, py::object tail) {
     check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
     TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
@@ -318,19 +339,48 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(params.device());
     const float* ax = nullptr;
     if (aux.has_value()) { TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == torch::kFloat32 && aux->numel() >= 13000); ax = aux->data_ptr<float>(); }
+    // fused tail (gradient exchange + SGD inside the step kernel):
+    //   tail = (grad_ptrs, inbox_ptrs, momentum, lr, mu, scale, rank, world, ticket, loss_snapshot | None)
+    FusedTailHost th;
+    const void* tp = nullptr;
+    if (!tail.is_none()) {
+      auto t = tail.cast<py::tuple>();
+      TORCH_CHECK(t.size() == 10, "tail: 10-tuple");
+      TORCH_CHECK(g != nullptr && st != nullptr && la != nullptr, "the fused tail needs grads, a step counter and loss_acc");
+      auto gp = t[0].cast<std::vector<unsigned long long>>();
+      auto ib = t[1].cast<std::vector<unsigned long long>>();
+      auto mom = t[2].cast<torch::Tensor>();
+      auto tick = t[8].cast<torch::Tensor>();
+      std::memset(&th, 0, sizeof(th));
+      th.world = t[7].cast<int>(); th.rank = t[6].cast<int>();
+      TORCH_CHECK((int)gp.size() == std::max(1, th.world) && (th.world == 1 || (int)ib.size() == th.world), "tail: one bucket / inbox pointer per rank");
+      for (size_t i = 0; i < gp.size() && i < 8; ++i) th.grad_ptrs[i] = (void*)(uintptr_t)gp[i];
+      for (size_t i = 0; i < ib.size() && i < 8; ++i) th.inbox_ptrs[i] = (void*)(uintptr_t)ib[i];
+      check_cuda_contig(mom, "momentum");
+      TORCH_CHECK(mom.scalar_type() == torch::kFloat32 && mom.numel() == params.numel());
+      TORCH_CHECK(tick.is_cuda() && tick.scalar_type() == torch::kInt32 && tick.numel() >= 2, "ticket: CUDA int32 [2]");
+      th.params = params.data_ptr<float>(); th.momentum = mom.data_ptr<float>();
+      th.step = const_cast<unsigned long long*>(st);
+      th.aux = const_cast<float*>(ax); th.loss_acc = la;
+      th.loss_snapshot = t[9].is_none() ? nullptr : t[9].cast<torch::Tensor>().data_ptr<float>();
+      th.ticket = reinterpret_cast<unsigned int*>(tick.data_ptr());
+      th.lr = t[3].cast<float>(); th.mu = t[4].cast<float>(); th.scale = t[5].cast<float>();
+      tp = &th;
+    }
     if (cluster > 1) {
       TORCH_CHECK(cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 1, 2, 4 or 8");
       ck_cuda(b2_convnet_cluster_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                         la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                        cluster, max_ctas, grad_stride, ax, cur_stream()), "convnet_cluster launch");
+                                        cluster, max_ctas, grad_stride, ax, tp, cur_stream()), "convnet_cluster launch");
       return;
     }
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                   max_ctas, grad_stride, ax, cur_stream()), "convnet_step launch");
+                                   max_ctas, grad_stride, ax, tp, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
-     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none());
+     py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none(),
+     py::arg("tail") = py::none());
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });
@@ -363,7 +413,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // bufs: [P1, P2, H, DH, dP2, DC, W2K, W2R, W3K, W3T, A1, A2, Hrelu, DLOG, G1, B3P] (see ops/convnet_batched.py)
   auto bt_bufs = [](const std::vector<torch::Tensor>& v, int64_t B) {
     TORCH_CHECK(v.size() == 16, "bufs: 16 tensors");
-    const int64_t need[16] = {B * 3072, B * 320, B * 64, B * 64, B * 320, B * 2048, 32 * 448, 400 * 64, 64 * 320, 320 * 64,
+    const int64_t need[16] = {B * 2304, B * 320, B * 64, B * 64, B * 320, B * 2048, 32 * 448, 400 * 64, 64 * 320, 320 * 64,
                               B * 1440, B * 320, B * 64, B * 16, B * 1440, 64};
     for (int i = 0; i < 16; ++i) {
       TORCH_CHECK(v[i].is_cuda() && v[i].is_contiguous() && v[i].numel() >= need[i], "bufs[", i, "] too small / not CUDA");
@@ -446,15 +496,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
                     int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int,
-                    std::vector<unsigned long long>, torch::Tensor>(),
+                    std::vector<unsigned long long>, torch::Tensor, bool, torch::Tensor>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
            py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::arg("chunk") = 1,
-           py::arg("inbox") = std::vector<unsigned long long>(), py::arg("loss_hist") = torch::Tensor(), py::keep_alive<1, 2>())
+           py::arg("inbox") = std::vector<unsigned long long>(), py::arg("loss_hist") = torch::Tensor(), py::arg("fused_tail") = false,
+           py::arg("ticket") = torch::Tensor(), py::keep_alive<1, 2>())
       .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
       .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
+      .def("stats", [](ExecutorPy& e) {
+        const auto& s = e.impl->stats();
+        py::dict d;
+        d["next_us"] = s.next_ns / 1e3; d["copy_wait_us"] = s.copy_wait_ns / 1e3; d["retire_us"] = s.retire_ns / 1e3;
+        d["total_us"] = s.total_ns / 1e3; d["chunk_steps"] = s.chunk_steps; d["single_steps"] = s.single_steps;
+        return d;
+      })
+      .def("reset_stats", [](ExecutorPy& e) { e.impl->reset_stats(); })
       .def("run", &ExecutorPy::run, py::arg("max_steps") = -1)
       .def("drain", [](ExecutorPy& e) { py::gil_scoped_release nogil; e.impl->drain(); })
       .def("last_loss_cumulative", [](ExecutorPy& e) { return e.impl->last_loss_cumulative(); });

@@ -717,6 +717,8 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
     atomicAdd(a.loss_acc + 1, (float)s.correct_local);
   }
+  // ------------------------------------------------------------------ fused tail: gradient exchange + SGD in this kernel
+  if (a.tail.enabled && a.backward) b2::fused_tail(a.tail, step, (int)gridDim.x, (int)blockIdx.x);   // grid <= B: every CTA flushed
   if (TC) {
     tc::fence_before();
     __syncthreads();
@@ -744,7 +746,8 @@ int b2_convnet_get_tc() {
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream) {
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
+                           const cn::FusedTailHost* tail, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cn::Smem) + 1024;
   if (!configured) {
@@ -759,9 +762,16 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   a.mask_out = mask_out; a.step = step; a.seed = seed; a.sample_base = sample_base; a.B = B; a.x_u8 = x_u8;
   a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
   a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
+  cn::fill_tail(a.tail, backward ? tail : nullptr, grad_stride);
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
+  if (a.tail.enabled) {       // the tail's grid-wide check-in spins: every CTA must be resident (one CTA per SM)
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (grid > sms) grid = sms;                 // CTAs loop over samples (b += gridDim.x)
+  }
   static const int pdl = [] { const char* e = getenv("B200DIST_PDL"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

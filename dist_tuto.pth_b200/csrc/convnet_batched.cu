@@ -5,20 +5,23 @@
 // (global batch 128, train_dist.py:85).  At B >= 1024 per GPU the same network is throughput-bound, and 66 % of its MACs
 // are the three conv2 GEMMs (train_dist.py:59,66 and their backward), so here:
 //
-//   conv1 -> pool -> relu             bt_conv1_fwd     SIMT (K = 25: not GEMM-shaped); writes P1 as bf16 NCHW [B,16,12,16]
+//   conv1 -> pool -> relu             bt_conv1_fwd     SIMT (K = 25: not GEMM-shaped); writes P1 as bf16 NHWC [B,12,12,16]
 //   conv2 -> dropout2d -> pool -> relu bt_conv2_fwd    tcgen05: implicit GEMM, M = 128 rows = 2 samples x 64 positions,
 //                                                       N = 32 (20 channels), K = 25 taps x 16 input channels.  TMA IS the
-//                                                       im2col: one 4-D box {8 x, 8 y, 16 c, 2 b} per tap at offset (kx, ky)
-//                                                       lands as an MN-major 128B-swizzled A tile; bias/dropout2d/pool/relu
-//                                                       run in the tcgen05.ld epilogue.
+//                                                       im2col: one 4-D box {16 c, 8 x, 8 y, 2 b} per tap at offset (kx, ky)
+//                                                       lands as a K-major 32B-swizzled A tile (one 32-byte row per output
+//                                                       position); bias/dropout2d/pool/relu run in the tcgen05.ld epilogue.
+//                                                       (Channel-last because TMA needs a 16-byte aligned innermost start:
+//                                                       an x-innermost box shifted by kx elements faults -- profiles/probes.)
 //   fc1 (+bias, relu)                  gemm_tcgen05.cu  the library GEMM of this repo (TMA + tcgen05), N = 64
 //   dropout, fc2, log_softmax, nll,    bt_head          SIMT, one thread per sample (2 kFLOP/sample)
 //   and their backward down to dH
 //   fc1 data gradient                  gemm_tcgen05.cu  dP2 = dH x W3
 //   pool/relu/dropout2d backward       bt_route         dP2 -> dC (bf16, NCHW [B,32,8,8])
-//   conv2 weight (+bias) gradient      bt_conv2_wgrad   tcgen05: D[(tap,ci), co] = sum over positions; 25 TMA tap boxes per
-//                                                       sample are the K-major A operand, dC the K-major B operand;
-//                                                       the bias gradient falls out of a constant-one input channel.
+//   conv2 weight (+bias) gradient      bt_conv2_wgrad   tcgen05: D[(tap,ci), co] = sum over positions; the same 25 TMA tap
+//                                                       boxes per sample are now the MN-major A operand (M = 8 taps x 16
+//                                                       channels per instruction), dC the K-major B operand; the bias
+//                                                       gradient falls out of a constant-one input channel.
 //   conv2 data gradient                bt_conv2_dgrad   tcgen05: dA[pos, (tap,ci)] = dC x W2 (N = 400 as 208 + 192), then
 //                                                       col2im + relu/pool routing of conv1 in the epilogue
 //   conv1 weight gradient              bt_conv1_wgrad   SIMT (sparse: one of four positions per pooled cell)
@@ -47,7 +50,7 @@ namespace bt {
 
 using cn::W1; using cn::B1; using cn::W2; using cn::B2; using cn::W3; using cn::B3; using cn::W4; using cn::B4;
 
-constexpr int P1_SAMPLE = 16 * 12 * 16;       // bf16 elements per sample of P1 [16 c][12 y][16 x]
+constexpr int P1_SAMPLE = 12 * 12 * 16;       // bf16 elements per sample of P1 [12 y][12 x][16 c] (channels 10..15: 1, 0, 0, 0, 0, 0)
 constexpr int DC_SAMPLE = 32 * 64;            // bf16 elements per sample of dC [32 co][64 pos]
 constexpr int W2K_K = 448;                    // 28 taps x 16 channels (25 real taps)
 constexpr int W2R_N = 400;                    // 25 taps x 16 channels
@@ -79,18 +82,15 @@ __global__ void __launch_bounds__(288) bt_conv1_fwd(const float* __restrict__ pa
                                                     unsigned char* __restrict__ A1) {
   __shared__ __align__(16) float xs[2][28 * 28];
   __shared__ __align__(16) float w1s[10][28];                       // 25 weights + bias + pad
-  __shared__ __align__(16) unsigned short p1s[2][10][12][16];       // bf16 bits, x padded to 16 (pad written once: zero)
-  __shared__ __align__(16) unsigned char a1s[2][1440];
   const int tid = threadIdx.x;
   for (int i = tid; i < 280; i += 288) {
     const int c = i / 28, k = i % 28;
     w1s[c][k] = k < 25 ? params[W1 + c * 25 + k] : (k == 25 ? params[B1 + c] : 0.f);
   }
-  for (int i = tid; i < 2 * 10 * 12 * 16; i += 288) reinterpret_cast<unsigned short*>(p1s)[i] = 0;
   const int sl = tid / 144, pos = tid % 144, py = pos / 12, px = pos % 12;
   for (int pair = blockIdx.x; pair * 2 < B; pair += gridDim.x) {
     const int b0 = pair * 2;
-    __syncthreads();                                                // previous iteration's stores are done with xs/p1s
+    __syncthreads();                                                // previous iteration is done with xs
     if (x_u8) {
       for (int i = tid; i < 98; i += 288) {                         // 2 x 49 uint4
         const int s = i / 49, q = i % 49;
@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(288) bt_conv1_fwd(const float* __restrict__ pa
           const float2 q = *reinterpret_cast<const float2*>(&xs[sl][(2 * py + i) * 28 + 2 * px + 2 * j]);
           patch[i][2 * j] = q.x; patch[i][2 * j + 1] = q.y;
         }
-#pragma unroll 1
+      float outv[10];
+      unsigned char* a1 = A1 + (size_t)(b0 + sl) * 1440 + pos;
+#pragma unroll
       for (int c = 0; c < 10; ++c) {
         float w[28];
 #pragma unroll
@@ -142,19 +144,14 @@ __global__ void __launch_bounds__(288) bt_conv1_fwd(const float* __restrict__ pa
         if (a01 > m) { m = a01; arg = 1; }
         if (a10 > m) { m = a10; arg = 2; }
         if (a11 > m) { m = a11; arg = 3; }
-        p1s[sl][c][py][px] = bf16_bits(fmaxf(m, 0.f));
-        a1s[sl][c * 144 + pos] = (unsigned char)(arg | (m > 0.f ? 0 : 4));
+        outv[c] = fmaxf(m, 0.f);
+        a1[c * 144] = (unsigned char)(arg | (m > 0.f ? 0 : 4));     // consecutive threads -> consecutive bytes
       }
-    }
-    __syncthreads();
-    for (int i = tid; i < 480; i += 288) {                          // 2 samples x 10 c x 12 y rows of 32 B (2 uint4)
-      const int s = i / 240, r = (i % 240) >> 1, h = i & 1;         // r = c*12 + y
-      if (b0 + s < B)
-        reinterpret_cast<uint4*>(P1 + (size_t)(b0 + s) * P1_SAMPLE + r * 16)[h] = reinterpret_cast<const uint4*>(&p1s[s][0][0][0] + r * 16)[h];
-    }
-    for (int i = tid; i < 180; i += 288) {                          // 2 x 90 uint4
-      const int s = i / 90, q = i % 90;
-      if (b0 + s < B) reinterpret_cast<uint4*>(A1 + (size_t)(b0 + s) * 1440)[q] = reinterpret_cast<const uint4*>(a1s[s])[q];
+      // one 32-byte NHWC pixel: 10 channels, the constant-one channel (conv2 bias-gradient row), 5 zero channels
+      uint4* dst = reinterpret_cast<uint4*>(P1 + (size_t)(b0 + sl) * P1_SAMPLE + pos * 16);
+      dst[0] = make_uint4(b2::pack_bf16x2(outv[0], outv[1]), b2::pack_bf16x2(outv[2], outv[3]), b2::pack_bf16x2(outv[4], outv[5]),
+                          b2::pack_bf16x2(outv[6], outv[7]));
+      dst[1] = make_uint4(b2::pack_bf16x2(outv[8], outv[9]), b2::pack_bf16x2(1.f, 0.f), 0u, 0u);
     }
   }
 }
@@ -162,10 +159,16 @@ __global__ void __launch_bounds__(288) bt_conv1_fwd(const float* __restrict__ pa
 // =====================================================================================================================
 // conv2 forward on tcgen05: implicit GEMM with TMA as the im2col engine.
 // =====================================================================================================================
-constexpr int C2F_NST = 16;
+// One TMA box per tile brings the whole 12x12x16 input of TWO samples into shared memory as [y][b][x][c] (32-byte pixels,
+// 32B swizzle); the 25 filter taps are then 25 shared-memory DESCRIPTORS over that image -- start address shifted by
+// (ky*768 + kx*32) bytes, 8-row groups (one output row of one sample) 384 bytes apart -- so the im2col costs no data movement
+// at all (the first version issued one TMA box per tap: 25x the L2->SM traffic, 70 us at B = 4096).  Accumulator row
+// r = (oy*2 + b)*8 + ox.  Descriptor arithmetic validated on hardware by scripts/tc_probe_matrix.py (umma_window_fwd_*).
+constexpr int C2F_NST = 4;
+constexpr int C2F_IMG = 12 * 2 * 12 * 32;     // 9216 B
 struct __align__(1024) C2fSmem {
   uint8_t w[7][4096];                 // W2 as B operand: 7 K-blocks of [32 co rows x 64 k], k = (tap % 4) * 16 + ci
-  uint8_t a[C2F_NST][4096];           // per tap: [2 b][16 ci][8 y][8 x] bf16 = MN-major A tile (M = b*64 + y*8 + x, K = ci)
+  uint8_t a[C2F_NST][C2F_IMG];        // [12 y][2 b][12 x][16 c] bf16
   float stage[128][21];
   float m2[2][20];
   float bias[20];
@@ -195,39 +198,39 @@ bt_conv2_fwd(const __grid_constant__ CUtensorMap map_p1, const __grid_constant__
   const uint32_t tmem0 = s.tmem_base;
 
   if (warp == 0) {
-    // ======================================================== TMA producer
+    // ======================================================== TMA producer: one box per tile
     if (lane == 0) {
       tc::mbar_expect_tx(&s.wfull, 7 * 4096);
       for (int j = 0; j < 7; ++j) tc::tma_load_2d(s.w[j], &map_w2k, &s.wfull, j * 64, 0);
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        for (int tap = 0; tap < 25; ++tap, ++it) {
-          const int st = it % C2F_NST;
-          tc::mbar_wait(&s.empty[st], ((it / C2F_NST) & 1) ^ 1);
-          tc::mbar_expect_tx(&s.full[st], 4096);
-          tc::tma_load_4d(s.a[st], &map_p1, &s.full[st], tap % 5, tap / 5, 0, 2 * t);   // (kx, ky, c0, b0): the im2col shift
-        }
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int st = it % C2F_NST;
+        tc::mbar_wait(&s.empty[st], ((it / C2F_NST) & 1) ^ 1);
+        tc::mbar_expect_tx(&s.full[st], C2F_IMG);
+        tc::tma_load_4d(s.a[st], &map_p1, &s.full[st], 0, 0, 2 * t, 0);       // dims (c, x, b, y)
       }
     }
   } else if (warp == 1) {
-    // ======================================================== MMA issuer
+    // ======================================================== MMA issuer: 25 taps = 25 descriptors over the image
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16_major(128, 32, /*A MN-major*/ 1, /*B K-major*/ 0);
+      constexpr uint32_t idesc = tc::idesc_bf16_major(128, 32, 0, 0);
       tc::mbar_wait(&s.wfull, 0);
-      uint32_t it = 0, li = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++li) {
-        const uint32_t acc = li & 1;
-        tc::mbar_wait(&s.tmem_empty[acc], ((li >> 1) & 1) ^ 1);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        const int st = it % C2F_NST;
+        tc::mbar_wait(&s.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc::mbar_wait(&s.full[st], (it / C2F_NST) & 1);
         tc::fence_after();
-        for (int tap = 0; tap < 25; ++tap, ++it) {
-          const int st = it % C2F_NST;
-          tc::mbar_wait(&s.full[st], (it / C2F_NST) & 1);
-          tc::fence_after();
-          const uint64_t ad = tc::smem_desc(tc::smem_u32(s.a[st]), /*LBO: next sample's 64 positions*/ 2048, /*SBO*/ 1024, 2);
+        const uint32_t img = tc::smem_u32(s.a[st]);
+#pragma unroll 5
+        for (int tap = 0; tap < 25; ++tap) {
+          const int ky = tap / 5, kx = tap - ky * 5;
+          const uint64_t ad = tc::smem_desc(img + ky * 768 + kx * 32, 16, /*SBO: next (oy, b) row group*/ 384, /*SWIZZLE_32B*/ 6);
           const uint64_t bd = tc::smem_desc(tc::smem_u32(s.w[tap >> 2]) + (tap & 3) * 32, 16, 1024, 2);
           tc::umma_bf16(tmem0 + acc * 32, ad, bd, idesc, tap > 0 ? 1u : 0u);
-          tc::commit(&s.empty[st]);
         }
+        tc::commit(&s.empty[st]);
         tc::commit(&s.tmem_full[acc]);
       }
     }
@@ -235,7 +238,8 @@ bt_conv2_fwd(const __grid_constant__ CUtensorMap map_p1, const __grid_constant__
   } else {
     // ======================================================== epilogue: bias, dropout2d, 2x2 max-pool, relu
     const int q = warp & 3, e = (warp - 2) * 32 + lane;          // q: TMEM lane quadrant this warp may read
-    const int r = q * 32 + lane, bl = r >> 6;                    // accumulator row = (sample in tile, position)
+    const int r = q * 32 + lane;                                 // accumulator row = (oy*2 + b)*8 + ox
+    const int bl = (r >> 3) & 1, srow = bl * 64 + (r >> 4) * 8 + (r & 7);   // staging row = b*64 + oy*8 + ox
     const float keep = 1.f / (1.f - cm.p_drop);
     const unsigned long long step = cm.step ? *cm.step : 0ull;
     uint32_t li = 0;
@@ -261,7 +265,7 @@ bt_conv2_fwd(const __grid_constant__ CUtensorMap map_p1, const __grid_constant__
       if (lane == 0) tc::mbar_arrive(&s.tmem_empty[acc]);         // accumulator drained: the issuer may start tile + 2
       tc::named_bar_sync(1, 128);                                 // m2 visible
 #pragma unroll
-      for (int co = 0; co < 20; ++co) s.stage[r][co] = (__uint_as_float(v[co]) + s.bias[co]) * s.m2[bl][co];
+      for (int co = 0; co < 20; ++co) s.stage[srow][co] = (__uint_as_float(v[co]) + s.bias[co]) * s.m2[bl][co];
       tc::named_bar_sync(1, 128);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -436,11 +440,17 @@ __global__ void __launch_bounds__(256) bt_route(const __nv_bfloat16* __restrict_
 
 // =====================================================================================================================
 // conv2 weight gradient on tcgen05:  D[(tap, ci), co] = sum_{b, pos} P1[b, ci, oy+ky, ox+kx] * dC[b, co, pos]
-// Both operands K-major (K = the 64 output positions of one sample): the A rows are 25 TMA tap boxes of 16 channel rows,
-// the B rows are the 32 channel rows of dC.  Input channel 10 of P1 is a constant 1 => row (tap 0, ci 10) is the bias gradient.
+// K = the 64 output positions of one sample.  A: the 25 TMA tap boxes [64 pos][16 ci] (32-byte rows, 32B swizzle) read
+// MN-major -- one instruction spans 8 taps (M = 128, atoms of 16 channels LBO = one tap tile apart).  B: the 32 channel rows of
+// dC, K-major.  Input channel 10 of P1 is a constant 1 => row (tap 0, ci 10) is the bias gradient.
 // =====================================================================================================================
-constexpr int WG_NST = 3;
-constexpr int WG_STAGE = 3 * 16384 + 8192 + 4096;     // three M = 128 blocks (8 taps each), one M = 64 block (tap 24), dC
+// One TMA box per sample brings its 12x12x16 input into shared memory as [y][x][c]; for each kernel row ky ONE instruction
+// covers the kernel columns kx = 0..7 x 16 channels as 8 MN-major atoms 32 bytes apart (atoms 5..7 read the pixels to the
+// right of the window: finite values whose output rows are never read), K = 16 output positions = two rows of the image.
+// 5 accumulators (one per ky) of [128 x 32].  Validated by scripts/tc_probe_matrix.py (umma_window_wgrad_*).
+constexpr int WG_NST = 8;
+constexpr int WG_IMG = 5120;                          // 4608-byte image + padding the out-of-window atoms may read
+constexpr int WG_STAGE = WG_IMG + 4096;               // + dC [32 co][64 pos]
 struct __align__(1024) WgSmem {
   uint8_t st[WG_NST][WG_STAGE];
   uint64_t full[WG_NST], empty[WG_NST], done;
@@ -453,17 +463,16 @@ bt_conv2_wgrad(const __grid_constant__ CUtensorMap map_p1, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   WgSmem& s = *reinterpret_cast<WgSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // rows 16..63 of the M = 64 block are never written by TMA: keep them zero
-  for (int stg = 0; stg < WG_NST; ++stg)
-    for (int i = threadIdx.x; i < (8192 - 2048) / 16; i += 192)
-      reinterpret_cast<uint4*>(s.st[stg] + 3 * 16384 + 2048)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int stg = 0; stg < WG_NST; ++stg)               // padding behind each image: finite (zero) forever
+    for (int i = threadIdx.x; i < (WG_IMG - 4608) / 16; i += 192)
+      reinterpret_cast<uint4*>(s.st[stg] + 4608)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&map_p1); tc::prefetch_tmap(&map_dc);
     for (int i = 0; i < WG_NST; ++i) { tc::mbar_init(&s.full[i], 1); tc::mbar_init(&s.empty[i], 1); }
     tc::mbar_init(&s.done, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc<128>(&s.tmem_base);
+  if (warp == 1) tc::tmem_alloc<256>(&s.tmem_base);
   tc::fence_proxy_async();
   tc::fence_before();
   __syncthreads();
@@ -476,29 +485,28 @@ bt_conv2_wgrad(const __grid_constant__ CUtensorMap map_p1, const __grid_constant
       for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
         const int st = it % WG_NST;
         tc::mbar_wait(&s.empty[st], ((it / WG_NST) & 1) ^ 1);
-        tc::mbar_expect_tx(&s.full[st], 25 * 2048 + 4096);
-        for (int tap = 0; tap < 25; ++tap)
-          tc::tma_load_4d(s.st[st] + (tap >> 3) * 16384 + (tap & 7) * 2048, &map_p1, &s.full[st], tap % 5, tap / 5, 0, b);
-        tc::tma_load_2d(s.st[st] + 3 * 16384 + 8192, &map_dc, &s.full[st], 0, 32 * b);
+        tc::mbar_expect_tx(&s.full[st], 4608 + 4096);
+        tc::tma_load_4d(s.st[st], &map_p1, &s.full[st], 0, 0, 0, b);                  // dims (c, x, y, b): the whole image
+        tc::tma_load_2d(s.st[st] + WG_IMG, &map_dc, &s.full[st], 0, 32 * b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id128 = tc::idesc_bf16_major(128, 32, 0, 0), id64 = tc::idesc_bf16_major(64, 32, 0, 0);
+      constexpr uint32_t idesc = tc::idesc_bf16_major(128, 32, 1, 0);
       uint32_t it = 0;
       for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
         const int st = it % WG_NST;
         tc::mbar_wait(&s.full[st], (it / WG_NST) & 1);
         tc::fence_after();
-        const uint32_t a0 = tc::smem_u32(s.st[st]), d0 = a0 + 3 * 16384 + 8192;
+        const uint32_t img = tc::smem_u32(s.st[st]), d0 = img + WG_IMG;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t bd = tc::smem_desc(d0 + ks * 32, 16, 1024, 2);
           const uint32_t accf = (it > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
-          for (int m = 0; m < 3; ++m)
-            tc::umma_bf16(tmem0 + m * 32, tc::smem_desc(a0 + m * 16384 + ks * 32, 16, 1024, 2), bd, id128, accf);
-          tc::umma_bf16(tmem0 + 96, tc::smem_desc(a0 + 3 * 16384 + ks * 32, 16, 1024, 2), bd, id64, accf);
+          for (int ky = 0; ky < 5; ++ky)
+            tc::umma_bf16(tmem0 + ky * 32, tc::smem_desc(img + ky * 384 + ks * 768, /*LBO: next kx*/ 32, /*SBO: next image row*/ 384, 6),
+                          bd, idesc, accf);
         }
         tc::commit(&s.empty[st]);
       }
@@ -509,29 +517,24 @@ bt_conv2_wgrad(const __grid_constant__ CUtensorMap map_p1, const __grid_constant
     const int q = warp & 3;
     tc::mbar_wait(&s.done, 0);
     tc::fence_after();
+    const int row = q * 32 + lane, kx = row >> 4, ci = row & 15;   // accumulator row = kx*16 + ci
 #pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
+    for (int ky = 0; ky < 5; ++ky) {
       uint32_t v[32];
-      tc::tmem_ld32(tmem0 + m * 32 + ((uint32_t)(q * 32) << 16), v);
+      tc::tmem_ld32(tmem0 + ky * 32 + ((uint32_t)(q * 32) << 16), v);
       tc::tmem_ld_wait();
-      int row;
-      if (m < 3) row = m * 128 + q * 32 + lane;
-      else row = (q == 0 && lane < 16) ? 384 + lane : -1;          // UMMA_M = 64: rows 0..15 are lanes 0..15 of quadrant 0
-      if (row >= 0) {
-        const int tap = row >> 4, ci = row & 15;
-        if (tap < 25 && ci < 10) {
+      if (kx < 5 && ci < 10) {
 #pragma unroll
-          for (int co = 0; co < 20; ++co) atomicAdd(grads + W2 + co * 250 + ci * 25 + tap, __uint_as_float(v[co]));
-        } else if (tap == 0 && ci == 10) {
+        for (int co = 0; co < 20; ++co) atomicAdd(grads + W2 + co * 250 + ci * 25 + ky * 5 + kx, __uint_as_float(v[co]));
+      } else if (ky == 0 && kx == 0 && ci == 10) {
 #pragma unroll
-          for (int co = 0; co < 20; ++co) atomicAdd(grads + B2 + co, __uint_as_float(v[co]));
-        }
+        for (int co = 0; co < 20; ++co) atomicAdd(grads + B2 + co, __uint_as_float(v[co]));
       }
     }
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 1) { tc::fence_after(); tc::tmem_dealloc<128>(tmem0); }
+  if (warp == 1) { tc::fence_after(); tc::tmem_dealloc<256>(tmem0); }
 }
 
 // =====================================================================================================================
@@ -549,7 +552,8 @@ struct __align__(1024) DgSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int DG_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two warps per TMEM lane quadrant)
+__global__ void __launch_bounds__(DG_THREADS, 1)
 bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant__ CUtensorMap map_w2r, int B,
                const unsigned char* __restrict__ A1, float* __restrict__ G1) {
   extern __shared__ uint8_t smem_raw[];
@@ -559,7 +563,7 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&map_dc); tc::prefetch_tmap(&map_w2r);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.full[i], 1); tc::mbar_init(&s.empty[i], 1); }
-    tc::mbar_init(&s.wfull, 1); tc::mbar_init(&s.acc_full, 1); tc::mbar_init(&s.acc_empty, 4);
+    tc::mbar_init(&s.wfull, 1); tc::mbar_init(&s.acc_full, 1); tc::mbar_init(&s.acc_empty, 8);
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(&s.tmem_base);
@@ -604,7 +608,8 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
     }
     __syncwarp();
   } else {
-    const int q = warp & 3, e = (warp - 2) * 32 + lane;
+    const int q = warp & 3, e = (warp - 2) * 32 + lane;            // e: 0..255
+    const int half = (warp - 2) >> 2;                              // warps 2..5 drain columns 0..191, warps 6..9 columns 192..399
     const int r = q * 32 + lane;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
@@ -613,7 +618,7 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
       tc::fence_after();
       uint8_t* myrow = s.stg + r * DG_ROW;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 384; c0 += 32) {
+      for (int c0 = half * 192; c0 < half * 192 + 192; c0 += 32) {
         uint32_t v[32];
         tc::tmem_ld32(tmem0 + (uint32_t)c0 + ((uint32_t)(q * 32) << 16), v);
         tc::tmem_ld_wait();
@@ -625,7 +630,7 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
                          b2::pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
                          b2::pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
       }
-      {
+      if (half == 1) {
         uint32_t v[16];
         tc::tmem_ld16(tmem0 + 384u + ((uint32_t)(q * 32) << 16), v);
         tc::tmem_ld_wait();
@@ -640,9 +645,9 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
       tc::fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s.acc_empty);
-      tc::named_bar_sync(1, 128);
+      tc::named_bar_sync(1, 256);
       // col2im gather: item = (sample in tile, y, x) of the 12 x 12 conv1 map
-      for (int item = e; item < 288; item += 128) {
+      for (int item = e; item < 288; item += 256) {
         const int sb = item / 144, p = item % 144, y = p / 12, x = p % 12;
         float acc[10];
 #pragma unroll
@@ -673,7 +678,7 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
           }
         }
       }
-      tc::named_bar_sync(1, 128);                                  // staging tile free for the next accumulator
+      tc::named_bar_sync(1, 256);                                  // staging tile free for the next accumulator
     }
   }
   tc::fence_before();
@@ -682,15 +687,23 @@ bt_conv2_dgrad(const __grid_constant__ CUtensorMap map_dc, const __grid_constant
 }
 
 // =====================================================================================================================
-// conv1 weight/bias gradient (sparse: the gradient of a pooled cell goes to its argmax position).  Warp = channel.
+// conv1 weight/bias gradient (sparse: the gradient of a pooled cell goes to its argmax position).
+// Lane = (cell in a group of 3, channel): the 30 active lanes of a warp read 5x5 windows that start within a few pixels of
+// each other, so the 25 shared-memory loads per item are (nearly) conflict-free -- the first version (lane = cell, warp =
+// channel) spread a warp's windows over three image rows and ran 4-way bank-conflicted (89 us at B = 4096).  Each lane keeps
+// the 25 taps + bias of ITS channel in registers over all samples of the CTA; one reduction at the end.
 // =====================================================================================================================
-__global__ void __launch_bounds__(320) bt_conv1_wgrad(const void* __restrict__ x, int x_u8, float mean, float inv_std,
-                                                      const float* __restrict__ G1, const unsigned char* __restrict__ A1,
-                                                      int B, float* __restrict__ grads) {
+constexpr int C1W_WARPS = 8;
+__global__ void __launch_bounds__(C1W_WARPS * 32) bt_conv1_wgrad(const void* __restrict__ x, int x_u8, float mean, float inv_std,
+                                                                  const float* __restrict__ G1, const unsigned char* __restrict__ A1,
+                                                                  int B, float* __restrict__ grads) {
+  constexpr int NT = C1W_WARPS * 32;
   __shared__ __align__(16) float xs[28 * 28 + 4];
-  __shared__ __align__(16) float gs[1440];
-  __shared__ __align__(16) unsigned char as[1440];
-  const int tid = threadIdx.x, c = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) float gs[144 * 11];             // [cell][channel], row stride 11: conflict-free for (3 cells x 10 ch)
+  __shared__ unsigned char as[144 * 11];
+  __shared__ float red[C1W_WARPS][10][26];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cl = lane / 10, c = lane - cl * 10;            // lanes 30, 31 idle
   float acc[25], bsum = 0.f;
 #pragma unroll
   for (int k = 0; k < 25; ++k) acc[k] = 0.f;
@@ -706,32 +719,43 @@ __global__ void __launch_bounds__(320) bt_conv1_wgrad(const void* __restrict__ x
     } else {
       if (tid < 196) reinterpret_cast<float4*>(xs)[tid] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (size_t)b * 784) + tid);
     }
-    for (int i = tid; i < 360; i += 320) reinterpret_cast<float4*>(gs)[i] = __ldg(reinterpret_cast<const float4*>(G1 + (size_t)b * 1440) + i);
-    if (tid >= 224 && tid < 314) reinterpret_cast<uint4*>(as)[tid - 224] = __ldg(reinterpret_cast<const uint4*>(A1 + (size_t)b * 1440) + tid - 224);
+    for (int i = tid; i < 1440; i += NT) {                 // coalesced read of [c][cell], transposed store
+      const int ch = i / 144, cell = i - ch * 144;
+      gs[cell * 11 + ch] = __ldg(G1 + (size_t)b * 1440 + i);
+      as[cell * 11 + ch] = __ldg(A1 + (size_t)b * 1440 + i);
+    }
     __syncthreads();
-    for (int cell = lane; cell < 144; cell += 32) {
-      const float g = gs[c * 144 + cell];
-      if (g != 0.f) {
-        const int arg = as[c * 144 + cell] & 3;
-        const float* src = &xs[(2 * (cell / 12) + (arg >> 1)) * 28 + 2 * (cell % 12) + (arg & 1)];
-        bsum += g;
+    if (lane < 30) {
+      for (int cg = warp; cg < 48; cg += C1W_WARPS) {      // 48 groups of 3 consecutive cells
+        const int cell = cg * 3 + cl;
+        const float g = gs[cell * 11 + c];
+        if (g != 0.f) {
+          const int arg = as[cell * 11 + c] & 3;
+          const float* src = &xs[(2 * (cell / 12) + (arg >> 1)) * 28 + 2 * (cell % 12) + (arg & 1)];
+          bsum += g;
 #pragma unroll
-        for (int ky = 0; ky < 5; ++ky)
+          for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 5; ++kx) acc[ky * 5 + kx] = fmaf(g, src[ky * 28 + kx], acc[ky * 5 + kx]);
+            for (int kx = 0; kx < 5; ++kx) acc[ky * 5 + kx] = fmaf(g, src[ky * 28 + kx], acc[ky * 5 + kx]);
+        }
       }
     }
   }
+  // lanes c, c + 10, c + 20 hold the same channel: fold them, then fold the warps, then one atomic per output per CTA
 #pragma unroll
-  for (int k = 0; k < 25; ++k) {
-    float v = acc[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) atomicAdd(grads + W1 + c * 25 + k, v);
+  for (int k = 0; k < 26; ++k) {
+    float v = k < 25 ? acc[k < 25 ? k : 0] : bsum;
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 10), v2 = __shfl_down_sync(0xffffffffu, v, 20);
+    if (lane < 10) red[warp][lane][k] = v + v1 + v2;
   }
+  __syncthreads();
+  for (int i = tid; i < 260; i += NT) {
+    const int ch = i / 26, k = i - ch * 26;
+    float v = 0.f;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, d);
-  if (lane == 0) atomicAdd(grads + B1 + c, bsum);
+    for (int w = 0; w < C1W_WARPS; ++w) v += red[w][ch][k];
+    atomicAdd(grads + (k < 25 ? W1 + ch * 25 + k : B1 + ch), v);
+  }
 }
 
 // =====================================================================================================================
@@ -813,9 +837,11 @@ __global__ void __launch_bounds__(512) bt_fc_wgrad(const __nv_bfloat16* __restri
   }
   if (tid < 400) {
 #pragma unroll
-    for (int jj = 0; jj < 5; ++jj)
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) atomicAdd(grads + W3 + (jg * 5 + jj) * 320 + ig * 8 + ii, acc[jj * 8 + ii]);
+    for (int jj = 0; jj < 5; ++jj) {                    // W3 + j*320 + ig*8 is 16-byte aligned (W3 = 5284 = 4 * 1321)
+      float* dst = grads + W3 + (jg * 5 + jj) * 320 + ig * 8;
+      cn::red_add_v4(dst, acc[jj * 8], acc[jj * 8 + 1], acc[jj * 8 + 2], acc[jj * 8 + 3]);
+      cn::red_add_v4(dst + 4, acc[jj * 8 + 4], acc[jj * 8 + 5], acc[jj * 8 + 6], acc[jj * 8 + 7]);
+    }
   } else {
 #pragma unroll
     for (int n = 0; n < 5; ++n) {
@@ -875,21 +901,37 @@ EncodeFn get_encode() {
   }();
   return fn;
 }
-bool encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+bool encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeFn enc = get_encode();
   if (!enc) { g_err = "cuTensorMapEncodeTiled not available (no CUDA driver?)"; return false; }
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return false; }
   return true;
 }
+// [y][b][x][c] image of two samples for the conv2-forward window descriptors: tensor dims ordered (c, x, b, y)
+bool map_p1_ybxc(CUtensorMap* m, const void* p1, int B) {
+  cuuint64_t dims[4] = {16, 12, (cuuint64_t)B, 12};
+  cuuint64_t strides[3] = {32, 12 * 12 * 32, 12 * 32};
+  cuuint32_t box[4] = {16, 12, 2, 12};
+  return encode(m, p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// whole [y][x][c] image of one sample (conv2 weight gradient)
+bool map_p1_image(CUtensorMap* m, const void* p1, int B) {
+  cuuint64_t dims[4] = {16, 12, 12, (cuuint64_t)B};
+  cuuint64_t strides[3] = {32, 12 * 32, 12 * 12 * 32};
+  cuuint32_t box[4] = {16, 12, 12, 1};
+  return encode(m, p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
 bool map_p1(CUtensorMap* m, const void* p1, int B, int box_b) {
-  cuuint64_t dims[4] = {16, 12, 16, (cuuint64_t)B};
-  cuuint64_t strides[3] = {32, 12 * 32, 16 * 12 * 32};
-  cuuint32_t box[4] = {8, 8, 16, (cuuint32_t)box_b};
-  return encode(m, p1, 4, dims, strides, box);
+  // NHWC [B][12 y][12 x][16 c]: the innermost box start (channel 0) is always 16-byte aligned; kx / ky shift dims 1 / 2
+  cuuint64_t dims[4] = {16, 12, 12, (cuuint64_t)B};
+  cuuint64_t strides[3] = {32, 12 * 32, 12 * 12 * 32};
+  cuuint32_t box[4] = {16, 8, 8, (cuuint32_t)box_b};
+  return encode(m, p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 bool map_rows(CUtensorMap* m, const void* ptr, long long rows, int cols, int box_rows) {   // [rows][cols] bf16, box {64, box_rows}
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -962,7 +1004,7 @@ int b2_bt_step_launch(const float* params, float* grads, const void* x, int x_u8
   const float mean = 0.1307f, inv_std = 1.f / 0.3081f;
   const int sms = sm_count();
   CUtensorMap m_p1_2, m_p1_1, m_w2k, m_dc64, m_dc32, m_w2r;
-  if (!map_p1(&m_p1_2, bf->P1, B, 2) || !map_p1(&m_p1_1, bf->P1, B, 1) || !map_rows(&m_w2k, bf->W2K, 32, W2K_K, 32) ||
+  if (!map_p1_ybxc(&m_p1_2, bf->P1, B) || !map_p1_image(&m_p1_1, bf->P1, B) || !map_rows(&m_w2k, bf->W2K, 32, W2K_K, 32) ||
       !map_rows(&m_dc64, bf->DC, (long long)B * 32, 64, 64) || !map_rows(&m_dc32, bf->DC, (long long)B * 32, 64, 32) ||
       !map_rows(&m_w2r, bf->W2R, W2R_N, 64, 200))
     return -3;
@@ -993,25 +1035,39 @@ int b2_bt_step_launch(const float* params, float* grads, const void* x, int x_u8
     bt_route<<<(B * 20 + 255) / 256, 256, 0, stream>>>(bf->dP2, bf->A2, B, training ? 1.f / (1.f - p_drop) : 1.f, bf->DC);
     if (!ck("route")) return -4;
   }
+  // The four gradient kernels are independent after `route`.  Two branches (a side stream forked/joined with events; under
+  // graph capture they become parallel graph branches):  main: conv2_dgrad -> conv1_wgrad    side: fc_wgrad -> conv2_wgrad
+  // The SIMT kernels (small shared memory) co-reside with the tensor-core kernels (one 170-180 KB CTA per SM).
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool overlap = (stage_mask & 255) == 255;
+  if (overlap && side == nullptr) {
+    cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+  }
+  cudaStream_t s2 = overlap ? side : stream;
+  if (overlap) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(side, ev_fork, 0); }
+  if (stage_mask & 128) {
+    const int per = B >= 148 * 32 ? (B + 147) / 148 : 32;            // ~one CTA per SM; >= 32 samples amortise the final atomics
+    const int ctas = (B + per - 1) / per;
+    bt_fc_wgrad<<<ctas, 512, 0, s2>>>(bf->P2, bf->H, bf->DH, bf->DLOG, B, per, grads);
+    if (!ck("fc_wgrad")) return -4;
+  }
   if (stage_mask & 16) {
-    bt_conv2_wgrad<<<B < sms ? B : sms, 192, sm_wg, stream>>>(m_p1_1, m_dc32, B, grads);
+    bt_conv2_wgrad<<<B < sms ? B : sms, 192, sm_wg, s2>>>(m_p1_1, m_dc32, B, grads);
     if (!ck("conv2_wgrad")) return -4;
   }
   if (stage_mask & 32) {
     const int tiles = (B + 1) / 2;
-    bt_conv2_dgrad<<<tiles < sms ? tiles : sms, 192, sm_dg, stream>>>(m_dc64, m_w2r, B, bf->A1, bf->G1);
+    bt_conv2_dgrad<<<tiles < sms ? tiles : sms, DG_THREADS, sm_dg, stream>>>(m_dc64, m_w2r, B, bf->A1, bf->G1);
     if (!ck("conv2_dgrad")) return -4;
   }
   if (stage_mask & 64) {
-    bt_conv1_wgrad<<<B < sms * 2 ? B : sms * 2, 320, 0, stream>>>(x, x_u8, mean, inv_std, bf->G1, bf->A1, B, grads);
+    bt_conv1_wgrad<<<B < sms * 4 ? B : sms * 4, C1W_WARPS * 32, 0, stream>>>(x, x_u8, mean, inv_std, bf->G1, bf->A1, B, grads);
     if (!ck("conv1_wgrad")) return -4;
   }
-  if (stage_mask & 128) {
-    int per = 128;
-    int ctas = (B + per - 1) / per;
-    bt_fc_wgrad<<<ctas, 512, 0, stream>>>(bf->P2, bf->H, bf->DH, bf->DLOG, B, per, grads);
-    if (!ck("fc_wgrad")) return -4;
-  }
+  if (overlap) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(stream, ev_join, 0); }
   return 0;
 }
 

@@ -11,26 +11,28 @@
 // steps are outstanding; a retired step hands its slot back to the prefetch thread (loader.cpp).  The GIL is released
 // around run().
 //
-// Chunk pipeline (the default when the loader ring is deep enough: num_slots % K == 0, num_slots >= 3K): K consecutive steps
-// are THREE graph launches, one per stream, ordered by three events instead of 9 driver calls per step:
-//   copy stream    : graph of K H2D copy nodes   (the K pinned loader slots of a slot group -> device block group g)
-//   compute stream : graph of 2K kernel nodes    (a pure kernel chain: programmatic dependent launch stays intact across the
-//                                                 K steps -- round 1's chunk graph had an H2D -> kernel edge in front of every
-//                                                 step, which cost as much as a graph boundary, profiles/executor_chunk_graphs.json)
-//   d2h stream     : graph of K D2H copy nodes   (the cumulative loss after each step, snapshotted on the device by that
-//                                                 step's SGD kernel into loss_hist[g*K + j], -> the step's pinned loss word)
-// Chunk c+1's copies run while chunk c computes (two device block groups), chunk c-1's losses drain meanwhile.  Every step
-// still has its own H2D copy from pinned memory and its own D2H read-back; the per-step path remains for the steps that do
-// not fill a chunk (epoch tails, max_steps budgets).
+// Chunk pipeline (the default when the loader ring is deep enough: num_slots >= 3K): K consecutive steps are issued together,
+//   copy stream    : K cudaMemcpyAsync H2D        (that step's pinned loader slot -> device block g*K + j), then ONE event
+//   compute stream : ONE graph of the K steps' kernels (a pure kernel chain: programmatic dependent launch stays intact across
+//                    the K steps -- round 1's chunk graph had an H2D -> kernel edge in front of every step, which cost as
+//                    much as a graph boundary, profiles/executor_chunk_graphs.json); captured once at construction
+//   d2h stream     : K cudaMemcpyAsync D2H        (the cumulative loss after each step, snapshotted on the device by that
+//                    step's optimizer tail into loss_hist[g*K + j] -> the step's pinned loss word)
+// ordered by three events per chunk.  Chunk c+1's copies run while chunk c computes (two device block groups g), chunk
+// c-1's losses drain meanwhile, and a loader slot goes back to the prefetch threads as soon as its H2D copy has completed
+// (not when the step retires), so staging never waits for the GPU.  Every step still has its own H2D copy from pinned
+// memory and its own D2H read-back; the per-step path remains for the steps that do not fill a chunk.
 #include "executor.h"
 
+#include <chrono>
 #include <cstring>
 
 extern "C" {
 int b2_convnet_step_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
-                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux, cudaStream_t stream);
+                           float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
+                           const void* tail, cudaStream_t stream);
 struct PeerPtrsC { void* p[8]; };
 struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
@@ -41,11 +43,28 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, cudaStream_t stream);
+                              const float* aux, const void* tail, cudaStream_t stream);
 int b2_convnet_npar();
+struct FusedTailHostC {            // mirrors cn::FusedTailHost (csrc/convnet_args.cuh)
+  void* grad_ptrs[8];
+  void* inbox_ptrs[8];
+  float* params;
+  float* momentum;
+  unsigned long long* step;
+  float* aux;
+  const float* loss_acc;
+  float* loss_snapshot;
+  unsigned int* ticket;
+  float lr, mu, scale;
+  int rank, world;
+};
 }
 
 namespace b2 {
+
+static inline long long now_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 StepExecutor::StepExecutor(const StepConfig& cfg, NativeLoader* loader, int max_in_flight)
     : cfg_(cfg), loader_(loader), max_in_flight_(max_in_flight < 1 ? 1 : max_in_flight) {
@@ -57,15 +76,15 @@ StepExecutor::StepExecutor(const StepConfig& cfg, NativeLoader* loader, int max_
     cudaEventCreateWithFlags(&kernels_done_[p], cudaEventDisableTiming);
   }
   const int K = cfg_.chunk, nb = loader_->num_slots();
-  chunk_ok_ = K >= 2 && K <= 8 && nb % K == 0 && nb >= 3 * K && cfg_.loss_hist != nullptr;
+  chunk_ok_ = K >= 2 && K <= 8 && nb >= 3 * K && cfg_.loss_hist != nullptr;
   if (chunk_ok_) {
-    h2d_exec_.assign(2 * (nb / K), nullptr);
-    d2h_exec_.assign(2 * (nb / K), nullptr);
     for (int g = 0; g < 2; ++g) {
       cudaEventCreateWithFlags(&h2d_done_[g], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&comp_done_[g], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&d2h_done_[g], cudaEventDisableTiming);
     }
+    copy_ev_.resize(nb / K + 2);
+    for (auto& e : copy_ev_) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   }
   slots_.resize(loader_->num_slots());
   for (auto& s : slots_) {
@@ -82,8 +101,7 @@ StepExecutor::~StepExecutor() {
     if (s.done) cudaEventDestroy(s.done);
     if (s.loss_pin) cudaFreeHost(s.loss_pin);
   }
-  for (auto g : h2d_exec_) if (g) cudaGraphExecDestroy(g);
-  for (auto g : d2h_exec_) if (g) cudaGraphExecDestroy(g);
+  for (auto e : copy_ev_) if (e) cudaEventDestroy(e);
   for (int g = 0; g < 2; ++g) {
     if (comp_exec_[g]) cudaGraphExecDestroy(comp_exec_[g]);
     if (h2d_done_[g]) cudaEventDestroy(h2d_done_[g]);
@@ -102,22 +120,36 @@ StepExecutor::~StepExecutor() {
 
 // Enqueues the two kernels of one step on the compute stream (called under stream capture).
 void StepExecutor::record_step(const void* x, const long long* y, float* loss_snapshot) {
+  FusedTailHostC th;
+  const void* tp = nullptr;
+  if (cfg_.fused_tail) {
+    std::memset(&th, 0, sizeof(th));
+    std::memcpy(th.grad_ptrs, cfg_.grad_ptrs, sizeof(th.grad_ptrs));
+    std::memcpy(th.inbox_ptrs, cfg_.inbox_ptrs, sizeof(th.inbox_ptrs));
+    th.params = cfg_.params; th.momentum = cfg_.momentum; th.step = cfg_.step_counter; th.aux = cfg_.aux;
+    th.loss_acc = cfg_.loss_acc; th.loss_snapshot = loss_snapshot; th.ticket = cfg_.ticket;
+    th.lr = cfg_.lr; th.mu = cfg_.mu; th.scale = 1.f / cfg_.world; th.rank = cfg_.rank; th.world = cfg_.world;
+    tp = &th;
+  }
   int rc = cfg_.cluster > 1
                ? b2_convnet_cluster_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                            cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1,
-                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, compute_)
+                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, tp, compute_)
                : b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                         cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
-                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, compute_);
-  PeerPtrsC g;
-  SignalPadsC sg;
-  std::memcpy(g.p, cfg_.grad_ptrs, sizeof(g.p));
-  std::memcpy(sg.pad, cfg_.sig_ptrs, sizeof(sg.pad));
-  PeerPtrsC ib;
-  std::memcpy(ib.p, cfg_.inbox_ptrs, sizeof(ib.p));
-  int rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
-                                    cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
-                                    cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, compute_);
+                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, tp, compute_);
+  int rc2 = 0;
+  if (!cfg_.fused_tail) {
+    PeerPtrsC g;
+    SignalPadsC sg;
+    std::memcpy(g.p, cfg_.grad_ptrs, sizeof(g.p));
+    std::memcpy(sg.pad, cfg_.sig_ptrs, sizeof(sg.pad));
+    PeerPtrsC ib;
+    std::memcpy(ib.p, cfg_.inbox_ptrs, sizeof(ib.p));
+    rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
+                                  cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
+                                  cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, compute_);
+  }
   if ((rc != 0 || rc2 != 0) && err_.empty())
     err_ = std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(rc ? rc : rc2));
 }
@@ -156,45 +188,63 @@ static bool end_capture(cudaStream_t st, cudaGraphExec_t* out, std::string* err,
   return true;
 }
 
-bool StepExecutor::capture_chunk(int sg, int g) {
+bool StepExecutor::capture_chunk(int g) {
   const int K = cfg_.chunk;
   err_.clear();
-  if (comp_exec_[g] == nullptr) {                      // 2K kernels: a pure chain, PDL intact from step to step
-    cudaError_t e = cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
-    for (int j = 0; j < K; ++j) {
-      unsigned char* blk = cfg_.in_dev[g * K + j];
-      record_step(blk, reinterpret_cast<const long long*>(blk + loader_->y_offset()), cfg_.loss_hist + 2 * (g * K + j));
-    }
-    if (!end_capture(compute_, &comp_exec_[g], &err_, "compute chunk")) return false;
+  if (comp_exec_[g] != nullptr) return true;           // K steps' kernels: a pure chain, PDL intact from step to step
+  cudaError_t e = cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
+  for (int j = 0; j < K; ++j) {
+    unsigned char* blk = cfg_.in_dev[g * K + j];
+    record_step(blk, reinterpret_cast<const long long*>(blk + loader_->y_offset()), cfg_.loss_hist + 2 * (g * K + j));
   }
-  if (h2d_exec_[sg * 2 + g] == nullptr) {              // K H2D copies, one per step, from that step's pinned loader slot
-    cudaError_t e = cudaStreamBeginCapture(copy_, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
-    for (int j = 0; j < K; ++j)
-      cudaMemcpyAsync(cfg_.in_dev[g * K + j], loader_->slot(sg * K + j).x, loader_->block_bytes(), cudaMemcpyHostToDevice, copy_);
-    if (!end_capture(copy_, &h2d_exec_[sg * 2 + g], &err_, "h2d chunk")) return false;
-  }
-  if (d2h_exec_[sg * 2 + g] == nullptr) {              // K D2H copies: the loss as of each step -> that step's pinned word
-    cudaError_t e = cudaStreamBeginCapture(d2h_, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
-    for (int j = 0; j < K; ++j)
-      cudaMemcpyAsync(slots_[sg * K + j].loss_pin, cfg_.loss_hist + 2 * (g * K + j), 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
-    if (!end_capture(d2h_, &d2h_exec_[sg * 2 + g], &err_, "d2h chunk")) return false;
-  }
+  return end_capture(compute_, &comp_exec_[g], &err_, "compute chunk");
+}
+
+// Captures (and instantiates) every graph the hot loop replays, so that no capture lands inside a timed / training region.
+bool StepExecutor::prepare() {
+  for (int p = 0; p < 2; ++p)
+    if (exec_[p] == nullptr && !capture(p)) return false;
+  if (chunk_ok_)
+    for (int g = 0; g < 2; ++g)
+      if (!capture_chunk(g)) { chunk_ok_ = false; chunk_note_ = err_; err_.clear(); break; }
   return true;
+}
+
+// Hand loader slots whose H2D copy has completed back to the prefetch threads (in hand-out order).
+void StepExecutor::release_copied(bool block_for_one) {
+  while (!copy_q_.empty()) {
+    const CopyFlight& c = copy_q_.front();
+    if (block_for_one) {
+      const long long t0 = now_ns();
+      cudaEventSynchronize(copy_ev_[c.ev]);
+      stats_.copy_wait_ns += now_ns() - t0;
+      block_for_one = false;
+    }
+    else if (cudaEventQuery(copy_ev_[c.ev]) != cudaSuccess) { cudaGetLastError(); break; }
+    for (int j = 0; j < c.count; ++j) loader_->release();
+    held_ -= c.count;
+    copy_q_.pop_front();
+  }
 }
 
 void StepExecutor::retire_oldest() {
   const Flight f = in_flight_.front();
   in_flight_.pop_front();
+  const long long t0 = now_ns();
   cudaEventSynchronize(slots_[f.ev_slot].done);
+  stats_.retire_ns += now_ns() - t0;
   const int s = f.slot;
   last_loss_ = (double)slots_[s].loss_pin[0];      // host read of this step's D2H loss copy
-  loader_->release();
+  if (!f.released_at_copy) loader_->release();
+}
+
+void StepExecutor::drain_copies() {
+  while (!copy_q_.empty()) release_copied(true);
 }
 
 void StepExecutor::drain() {
+  drain_copies();
   while (!in_flight_.empty()) retire_oldest();
 }
 
@@ -204,58 +254,66 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
   *epoch_done = 0;
   int64_t done = 0;
   const int K = cfg_.chunk, nb = loader_->num_slots();
+  struct Total { long long t0; Stats* s; ~Total() { s->total_ns += now_ns() - t0; } } total{now_ns(), &stats_};
   while (max_steps < 0 || done < max_steps) {
-    // ---- chunk path: K full batches ahead, slot group aligned, budget allows
-    if (chunk_ok_ && (max_steps < 0 || max_steps - done >= K) && loader_->consumed() % K == 0 &&
-        loader_->full_batches_left() >= K) {
-      while ((int)in_flight_.size() > nb - K) retire_oldest();     // the prefetch thread needs K free slots to fill
-      const int sg = (int)((loader_->consumed() % nb) / K);
+    // ---- chunk path: K full batches ahead and the budget allows
+    if (chunk_ok_ && (max_steps < 0 || max_steps - done >= K) && loader_->full_batches_left() >= K) {
       const int g = (int)(chunks_issued_ & 1);
-      if ((comp_exec_[g] == nullptr || h2d_exec_[sg * 2 + g] == nullptr || d2h_exec_[sg * 2 + g] == nullptr) &&
-          !capture_chunk(sg, g)) {
+      if (comp_exec_[g] == nullptr && !capture_chunk(g)) {
         chunk_ok_ = false;
         chunk_note_ = err_;
         err_.clear();
         continue;
       }
-      int first = -1;
-      for (int j = 0; j < K; ++j) {                                 // blocks until the K batches are staged
-        int64_t count = 0;
-        const int slot = loader_->next(&count);
-        if (j == 0) first = slot;
-        if (slot != sg * K + j || count != cfg_.B) { err_ = "chunk path: loader slot sequence broke"; return -1; }
-      }
+      release_copied(false);
+      while (held_ > nb - K) release_copied(true);                  // the prefetch threads need K free slots to stage into
+      while ((int)in_flight_.size() > nb - K) retire_oldest();      // a slot's pinned loss word is reused nb steps later
       // copies: device block group g is free once the chunk that last read it (two chunks ago) has computed; blocks 0/1
       // are also the per-step path's double buffer
       cudaStreamWaitEvent(copy_, comp_done_[g], 0);
       cudaStreamWaitEvent(copy_, kernels_done_[0], 0);
       cudaStreamWaitEvent(copy_, kernels_done_[1], 0);
-      cudaError_t e = cudaGraphLaunch(h2d_exec_[sg * 2 + g], copy_);
-      if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch(h2d chunk): ") + cudaGetErrorString(e); return -1; }
+      int slot_of[8];
+      for (int j = 0; j < K; ++j) {                                 // blocks until batch j is staged
+        int64_t count = 0;
+        const long long tn = now_ns();
+        const int slot = loader_->next(&count);
+        stats_.next_ns += now_ns() - tn;
+        if (slot < 0 || count != cfg_.B) { err_ = "chunk path: loader handed out a short batch"; return -1; }
+        slot_of[j] = slot;
+        cudaMemcpyAsync(cfg_.in_dev[g * K + j], loader_->slot(slot).x, loader_->block_bytes(), cudaMemcpyHostToDevice, copy_);
+      }
+      const int ev = (int)(chunks_issued_ % (int64_t)copy_ev_.size());
+      cudaEventRecord(copy_ev_[ev], copy_);
       cudaEventRecord(h2d_done_[g], copy_);
+      copy_q_.push_back({ev, K});
+      held_ += K;
       // kernels: after the copies, and after the losses of the chunk that last used snapshot group g have been read back
       cudaStreamWaitEvent(compute_, h2d_done_[g], 0);
       cudaStreamWaitEvent(compute_, d2h_done_[g], 0);
-      e = cudaGraphLaunch(comp_exec_[g], compute_);
+      cudaError_t e = cudaGraphLaunch(comp_exec_[g], compute_);
       if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch(compute chunk): ") + cudaGetErrorString(e); return -1; }
       cudaEventRecord(comp_done_[g], compute_);
       if (g == 0) { cudaEventRecord(kernels_done_[0], compute_); cudaEventRecord(kernels_done_[1], compute_); }
       // losses
       cudaStreamWaitEvent(d2h_, comp_done_[g], 0);
-      e = cudaGraphLaunch(d2h_exec_[sg * 2 + g], d2h_);
-      if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch(d2h chunk): ") + cudaGetErrorString(e); return -1; }
+      for (int j = 0; j < K; ++j)
+        cudaMemcpyAsync(slots_[slot_of[j]].loss_pin, cfg_.loss_hist + 2 * (g * K + j), 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
       cudaEventRecord(d2h_done_[g], d2h_);
-      const int last = first + K - 1;
-      cudaEventRecord(slots_[last].done, d2h_);
-      for (int j = 0; j < K; ++j) in_flight_.push_back({first + j, last});
+      cudaEventRecord(slots_[slot_of[K - 1]].done, d2h_);
+      for (int j = 0; j < K; ++j) in_flight_.push_back({slot_of[j], slot_of[K - 1], true});
       ++chunks_issued_;
       issued_ += K;
       done += K;
+      stats_.chunk_steps += K;
       continue;
     }
+    drain_copies();                                                 // per-step path below releases at retire: keep the order
     while ((int)in_flight_.size() >= max_in_flight_) retire_oldest();
     int64_t count = 0;
+    const long long tn1 = now_ns();
     const int slot = loader_->next(&count);
+    stats_.next_ns += now_ns() - tn1;
     if (slot < 0) { *epoch_done = 1; break; }
     if (count != cfg_.B) {            // short tail batch: give it back to the caller (eager path)
       drain();
@@ -279,9 +337,10 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
     cudaStreamWaitEvent(d2h_, kernels_done_[p], 0);
     cudaMemcpyAsync(slots_[slot].loss_pin, cfg_.loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
     cudaEventRecord(slots_[slot].done, d2h_);
-    in_flight_.push_back({slot, slot});
+    in_flight_.push_back({slot, slot, false});
     ++issued_;
     ++done;
+    ++stats_.single_steps;
   }
   return done;
 }

@@ -31,6 +31,8 @@ struct StepConfig {
   float* aux;                        // conv2.weight in the kernels' smem layouts (maintained by the SGD kernel)
   void* inbox_ptrs[8];               // push exchange (sgd.cu): every rank's inbox
   int push;
+  int fused_tail;                    // gradient exchange + SGD in the tail of the step kernel (one kernel per step)
+  unsigned int* ticket;              // device scratch of the fused tail
 };
 
 class StepExecutor {
@@ -42,9 +44,15 @@ class StepExecutor {
   // *epoch_done is set when the loader ran dry.
   int64_t run(int64_t max_steps, int* pending_slot, int64_t* pending_count, int* epoch_done);
   void drain();                      // wait for everything in flight, release loader slots
+  bool prepare();                    // capture every graph of the hot loop now (keeps captures out of timed regions)
   double last_loss_cumulative() const { return last_loss_; }
   const std::string& error() const { return err_; }
   bool chunking() const { return chunk_ok_; }
+  // host-side time accounting of run() (ns): where the feeding loop waits -- {loader next(), copy-event waits, loss retire
+  // waits, everything else (driver calls)}, and the number of chunked / single steps issued
+  struct Stats { long long next_ns = 0, copy_wait_ns = 0, retire_ns = 0, total_ns = 0, chunk_steps = 0, single_steps = 0; };
+  const Stats& stats() const { return stats_; }
+  void reset_stats() { stats_ = Stats(); }
   const std::string& chunk_note() const { return chunk_note_; }   // why chunk graphs were turned off (if they were)
 
  private:
@@ -53,7 +61,9 @@ class StepExecutor {
     float* loss_pin = nullptr;
   };
   bool capture(int parity);
-  bool capture_chunk(int slot_group, int g);
+  bool capture_chunk(int g);
+  void release_copied(bool block_for_one);
+  void drain_copies();
   void record_step(const void* x, const long long* y, float* loss_snapshot = nullptr);
   void retire_oldest();
   StepConfig cfg_;
@@ -65,16 +75,20 @@ class StepExecutor {
   std::vector<Slot> slots_;
   // chunk pipeline: K consecutive steps = three graph launches on three streams (see executor.cpp).  The slot of batch b is
   // b % num_slots, so the pinned addresses of a slot group are fixed; g = chunk parity selects the device block group.
-  std::vector<cudaGraphExec_t> h2d_exec_, d2h_exec_;   // [slot_group * 2 + g]
-  cudaGraphExec_t comp_exec_[2] = {nullptr, nullptr};
+  cudaGraphExec_t comp_exec_[2] = {nullptr, nullptr};  // the K steps' kernels reading device block group g
+  std::vector<cudaEvent_t> copy_ev_;                   // "H2D copies of chunk c are done" (ring)
+  struct CopyFlight { int ev, count; };
+  std::deque<CopyFlight> copy_q_;                      // chunks whose loader slots are still held
+  int held_ = 0;
   cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, comp_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
   int64_t chunks_issued_ = 0;
   bool chunk_ok_ = false;
-  struct Flight { int slot, ev_slot; };
+  struct Flight { int slot, ev_slot; bool released_at_copy; };
   std::deque<Flight> in_flight_;
   int64_t issued_ = 0;
   double last_loss_ = 0.0;
   std::string err_, chunk_note_;
+  Stats stats_;
 };
 
 }  // namespace b2

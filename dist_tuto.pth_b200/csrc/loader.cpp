@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <stdexcept>
@@ -29,6 +30,13 @@ NativeLoader::NativeLoader(const uint8_t* images, const int64_t* labels, int64_t
   y_offset_ = (xbytes + 255) / 256 * 256;          // one block per slot: [x | pad | y] -> ONE H2D copy per step
   block_bytes_ = y_offset_ + ybytes;
   slots_.resize(nbuf_);
+  staged_.assign(nbuf_, -1);
+  {
+    const char* e = getenv("B200DIST_LOADER_THREADS");
+    const unsigned hc = std::thread::hardware_concurrency();
+    nworkers_ = e ? atoi(e) : (hc >= 8 && batch_ >= 64 ? 2 : 1);
+    nworkers_ = std::max(1, std::min({nworkers_, 8, nbuf_ / 2}));
+  }
   for (auto& s : slots_) {
     if (pinned_) {
       if (cudaHostAlloc(&s.x, block_bytes_, cudaHostAllocDefault) != cudaSuccess) {
@@ -65,17 +73,24 @@ void NativeLoader::start_epoch(int64_t epoch) {
   }
   {
     std::lock_guard<std::mutex> lk(mu_);
-    produced_ = consumed_ = released_ = 0;
+    consumed_ = released_ = 0;
+    std::fill(staged_.begin(), staged_.end(), (int64_t)-1);
     stopping_ = false;
   }
-  worker_ = std::thread([this] { this->run(); });
+  for (int w = 0; w < nworkers_; ++w) workers_.emplace_back([this, w] { this->run(w); });
 }
 
 void NativeLoader::fill(Slot& s, int64_t b) {
   const int64_t n = (int64_t)order_.size();
   const int64_t lo = b * batch_, hi = std::min(n, lo + batch_);
   s.count = hi - lo;
+  constexpr int64_t kAhead = 6;      // a batch is a gather of random rows: keep the DRAM misses of the next rows in flight
   for (int64_t k = lo; k < hi; ++k) {
+    if (k + kAhead < hi) {
+      const uint8_t* nxt = images_ + order_[k + kAhead] * item_;
+      for (int64_t o = 0; o < item_; o += 64) __builtin_prefetch(nxt + o, 0, 0);
+      __builtin_prefetch(labels_ + order_[k + kAhead], 0, 0);
+    }
     const int64_t src = order_[k];
     const uint8_t* img = images_ + src * item_;
     if (raw_) {
@@ -89,18 +104,19 @@ void NativeLoader::fill(Slot& s, int64_t b) {
   }
 }
 
-void NativeLoader::run() {
+void NativeLoader::run(int worker) {
   const int64_t nb = num_batches();
-  for (int64_t b = 0; b < nb; ++b) {
+  for (int64_t b = worker; b < nb; b += nworkers_) {
     {
       std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return stopping_ || produced_ - released_ < nbuf_; });
+      // slot b % nbuf_ is free once the batch that used it before (b - nbuf_) has been released by the consumer
+      cv_.wait(lk, [&] { return stopping_ || b - released_ < nbuf_; });
       if (stopping_) return;
     }
     fill(slots_[b % nbuf_], b);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      ++produced_;
+      staged_[b % nbuf_] = b;
     }
     cv_.notify_all();
   }
@@ -112,9 +128,9 @@ int NativeLoader::next(int64_t* count) {
   const int64_t nb = num_batches();
   std::unique_lock<std::mutex> lk(mu_);
   if (consumed_ >= nb) return -1;
-  cv_.wait(lk, [&] { return stopping_ || produced_ > consumed_; });
-  if (stopping_) return -1;
   const int slot = (int)(consumed_ % nbuf_);
+  cv_.wait(lk, [&] { return stopping_ || staged_[slot] == consumed_; });
+  if (stopping_) return -1;
   *count = slots_[slot].count;
   ++consumed_;
   return slot;
@@ -144,7 +160,8 @@ void NativeLoader::stop() {
     stopping_ = true;
   }
   cv_.notify_all();
-  if (worker_.joinable()) worker_.join();
+  for (auto& w : workers_) if (w.joinable()) w.join();
+  workers_.clear();
 }
 
 }  // namespace b2

@@ -36,7 +36,7 @@ class NativeLoader {
   bool pinned() const { return pinned_; }
 
  private:
-  void run();
+  void run(int worker);
   void fill(Slot& s, int64_t b);
   const uint8_t* images_;
   const int64_t* labels_;
@@ -50,10 +50,14 @@ class NativeLoader {
   bool pinned_;
   size_t y_offset_ = 0, block_bytes_ = 0;
   std::vector<Slot> slots_;
-  std::thread worker_;
+  // `nworkers_` prefetch threads: worker w stages batches w, w + nworkers_, ... (a random-index gather of 128 x 784 B is
+  // DRAM-latency bound on one core: ~30 us per batch, i.e. slower than the GPU step); batches are handed out in order.
+  int nworkers_ = 1;
+  std::vector<std::thread> workers_;
+  std::vector<int64_t> staged_;      // per slot: index of the batch currently staged in it (-1: none)
   std::mutex mu_;
   std::condition_variable cv_;
-  int64_t produced_ = 0, consumed_ = 0, released_ = 0;
+  int64_t consumed_ = 0, released_ = 0;
   bool stopping_ = true;
 };
 

@@ -13,56 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"
+#include "sgd_device.cuh"
 
 namespace b2 {
-
-constexpr int kSgdThreads = 512;
-
-struct SgdArgs {
-  PeerPtrs grads;            // symmetric flat fp32 gradient buckets (grads.p[rank] is ours)
-  SignalPads sig;
-  float* params;
-  float* momentum;
-  unsigned long long* step;  // incremented once per call (may be null)
-  unsigned int* done_counter; // block-completion counter (device scratch, zero between calls)
-  size_t n_vec;              // float4 vectors
-  float lr, mu, scale;
-  int rank, world;
-  int zero_grads;
-  long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
-  float* aux;                // optional [w2f 5000 | w2b 8000]: conv2.weight re-arranged for the forward/backward kernels
-  PeerPtrs inbox;            // push variant only: every rank's inbox  [2 parities][world sources][n_vec][2 lines of 16 B]
-  const float* loss_acc;     // optional: the step kernels' running [sum of batch-mean nll, #correct] ...
-  float* loss_snapshot;      // ... copied here (2 floats) = the cumulative loss as of THIS step (per-step D2H source)
-};
-
-// The previous kernel of the stream (this step's forward/backward) is complete and the next step's kernel cannot pass its
-// own griddepcontrol.wait before this kernel ends, so loss_acc holds exactly the loss up to and including this step.
-__device__ __forceinline__ void snapshot_loss(const SgdArgs& a) {
-  if (a.loss_snapshot != nullptr && blockIdx.x == 0 && threadIdx.x < 2)
-    a.loss_snapshot[threadIdx.x] = *reinterpret_cast<const volatile float*>(a.loss_acc + threadIdx.x);
-}
-
-// SGD update of one float4 vector (+ the pre-arranged conv2.weight copies), shared by both exchange variants
-__device__ __forceinline__ void sgd_apply(const SgdArgs& a, size_t v, float4 g) {
-  g.x *= a.scale; g.y *= a.scale; g.z *= a.scale; g.w *= a.scale;
-  float4 m = reinterpret_cast<float4*>(a.momentum)[v];
-  float4 p = reinterpret_cast<float4*>(a.params)[v];
-  m.x = fmaf(a.mu, m.x, g.x); m.y = fmaf(a.mu, m.y, g.y); m.z = fmaf(a.mu, m.z, g.z); m.w = fmaf(a.mu, m.w, g.w);
-  p.x = fmaf(-a.lr, m.x, p.x); p.y = fmaf(-a.lr, m.y, p.y); p.z = fmaf(-a.lr, m.z, p.z); p.w = fmaf(-a.lr, m.w, p.w);
-  reinterpret_cast<float4*>(a.momentum)[v] = m;
-  reinterpret_cast<float4*>(a.params)[v] = p;
-  if (a.aux != nullptr && v >= 264 / 4 && v < (264 + 5000) / 4) {      // conv2.weight (flat offset 264, 5000 elements)
-    const float pw[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int i = (int)v * 4 + e - 264;
-      const int co = i / 250, r = i - co * 250, ci = r / 25, kk = r - ci * 25;
-      a.aux[(ci * 25 + kk) * 20 + co] = pw[e];                                     // w2f [ci][ky][kx][co]
-      a.aux[5000 + ((co * 25 + kk) * 2 + ci / 5) * 8 + ci % 5] = pw[e];            // w2b [co][ky][kx][half][8]
-    }
-  }
-}
 
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
   const int rank = a.rank, world = a.world;
@@ -136,7 +89,6 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
 // double-buffered by step parity: a peer can only write parity p again two steps later, which needs my push of the
 // step in between, which I issue after I finished reading parity p.
 __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs a) {
-  const int rank = a.rank, world = a.world;
   __shared__ unsigned long long s_step;
   pdl_wait();
   pdl_launch_dependents();
@@ -148,56 +100,8 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs
   }
   __syncthreads();
   const unsigned long long st = s_step;
-  const uint32_t epoch = (uint32_t)(st + 1ull);
-  const size_t par = (size_t)(st & 1ull);
-  const size_t cur_off = par * (size_t)a.grad_stride * sizeof(float);
-  const size_t oth_off = (par ^ 1) * (size_t)a.grad_stride * sizeof(float);
   const size_t stride = (size_t)gridDim.x * kSgdThreads;
-  for (size_t v = (size_t)blockIdx.x * kSgdThreads + threadIdx.x; v < a.n_vec; v += stride) {
-    const uint4 mine = ld_cg_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.grads.p[rank]) + cur_off) + v);
-    // line index inside an inbox: ((parity * world + source) * n_vec + v) * 2
-    const size_t dst_line = ((par * (size_t)world + (size_t)rank) * a.n_vec + v) * 2;
-    const uint4 l0 = make_uint4(mine.x, epoch, mine.y, epoch), l1 = make_uint4(mine.z, epoch, mine.w, epoch);
-#pragma unroll
-    for (int i = 1; i < B2_MAX_RANKS; ++i) {          // start with the next rank so the ranks do not all hit one peer first
-      if (i < world) {
-        int r = rank + i;
-        if (r >= world) r -= world;
-        uint4* dst = reinterpret_cast<uint4*>(a.inbox.p[r]) + dst_line;
-        st_volatile_v4(dst, l0);
-        st_volatile_v4(dst + 1, l1);
-      }
-    }
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint4* in = reinterpret_cast<const uint4*>(a.inbox.p[rank]);
-#pragma unroll
-    for (int r = 0; r < B2_MAX_RANKS; ++r) {
-      if (r < world) {
-        uint4 q0, q1;
-        if (r == rank) {
-          q0 = l0; q1 = l1;
-        } else {
-          const uint4* src = in + ((par * (size_t)world + (size_t)r) * a.n_vec + v) * 2;
-          unsigned long long spins = 0;
-          for (;;) {
-            q0 = ld_volatile_v4(src);
-            q1 = ld_volatile_v4(src + 1);
-            if (q0.y == epoch && q0.w == epoch && q1.y == epoch && q1.w == epoch) break;
-            if (++spins > B2_SPIN_LIMIT) {
-              printf("[b200dist] push all-reduce: rank %d timed out waiting for rank %d (step %llu, vector %llu)\n", rank, r, st,
-                     (unsigned long long)v);
-              __trap();
-            }
-          }
-        }
-        g.x += __uint_as_float(q0.x); g.y += __uint_as_float(q0.z);
-        g.z += __uint_as_float(q1.x); g.w += __uint_as_float(q1.z);
-      }
-    }
-    sgd_apply(a, v, g);
-    if (a.zero_grads)
-      st_cg_v4(reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.grads.p[rank]) + oth_off) + v, make_uint4(0u, 0u, 0u, 0u));
-  }
+  for (size_t v = (size_t)blockIdx.x * kSgdThreads + threadIdx.x; v < a.n_vec; v += stride) exchange_apply_vec(a, v, st);
   if (threadIdx.x == 0 && seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
 }
 

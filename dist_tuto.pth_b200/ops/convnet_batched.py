@@ -32,20 +32,20 @@ STAGES = {"conv1_fwd": 1, "conv2_fwd": 2, "head": 4, "fc1_dgrad": 8, "conv2_wgra
 class BatchedBuffers:
     """Activation / operand buffers of one batch size (bf16 unless noted); order = ``BtBuffers`` in csrc/bindings.cpp.
 
-    ``P1`` relu(pool(conv1)) as NCHW [B,16,12,16]: channels 10..15 and columns 12..15 are padding that makes every TMA
-    stride a multiple of 16 bytes; channel 10 is a constant 1 so that the conv2 bias gradient is one row of the weight-
-    gradient GEMM; ``DC`` conv2-output gradient [B,32,8,8] (channels 20..31 stay zero)."""
+    ``P1`` relu(pool(conv1)) channel-last [B,12,12,16] (one 32-byte pixel = one TMA row): channels 11..15 are zero padding,
+    channel 10 is a constant 1 so that the conv2 bias gradient is one row of the weight-gradient GEMM; ``DC`` conv2-output
+    gradient [B,32,8,8] (channels 20..31 stay zero)."""
 
     def __init__(self, B: int, device):
         bf, u8, f32 = torch.bfloat16, torch.uint8, torch.float32
         z = lambda n, dt: torch.zeros(n, dtype=dt, device=device)   # noqa: E731
         self.B = int(B)
-        self.P1, self.P2, self.H, self.DH, self.dP2 = z(B * 3072, bf), z(B * 320, bf), z(B * 64, bf), z(B * 64, bf), z(B * 320, bf)
+        self.P1, self.P2, self.H, self.DH, self.dP2 = z(B * 2304, bf), z(B * 320, bf), z(B * 64, bf), z(B * 64, bf), z(B * 320, bf)
         self.DC = z(B * 2048, bf)
         self.W2K, self.W2R, self.W3K, self.W3T = z(32 * 448, bf), z(400 * 64, bf), z(64 * 320, bf), z(320 * 64, bf)
         self.A1, self.A2 = z(B * 1440, u8), z(B * 320, u8)
         self.Hrelu, self.DLOG, self.G1, self.B3P = z(B * 64, f32), z(B * 16, f32), z(B * 1440, f32), z(64, f32)
-        self.P1.view(B, 16, 12, 16)[:, 10].fill_(1.0)             # the constant-one input channel (bias gradient row)
+        self.P1.view(B, 12, 12, 16)[..., 10].fill_(1.0)           # the constant-one input channel (bias gradient row)
 
     def as_list(self) -> List[torch.Tensor]:
         return [self.P1, self.P2, self.H, self.DH, self.dP2, self.DC, self.W2K, self.W2R, self.W3K, self.W3T,

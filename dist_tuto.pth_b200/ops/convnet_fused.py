@@ -183,7 +183,11 @@ class FusedTrainer:
         self._nstep = 0
         self._loss_read = 0.0                       # cumulative loss already returned by pop_loss_sum
         self._last_loss_cum = 0.0
-        self.gpu_launches_per_step = 2              # convnet_step + allreduce_sgd (our kernels)
+        # "one kernel per step": gradient exchange + SGD run in the tail of the step kernel (csrc/sgd_device.cuh: grid-wide
+        # check-in, then every CTA pushes / reduces / updates a share of the bucket).  Needs the push inbox when world > 1.
+        self.fused_tail = os.environ.get("B200DIST_FUSED_TAIL", "1") != "0" and (self.world == 1 or self.inbox_handle is not None)
+        self.ticket = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.gpu_launches_per_step = 1 if self.fused_tail else 2     # convnet_step (+ allreduce_sgd)
         self._warm()
 
     def _reset_exchange(self):
@@ -198,6 +202,8 @@ class FusedTrainer:
         self.grads.zero_()
         if self.inbox_handle is not None:
             self.inbox_handle.local.zero_()
+        if getattr(self, "ticket", None) is not None:
+            self.ticket.zero_()
         torch.cuda.synchronize(self.device)
         if self.world > 1:
             comm.barrier(self.group)
@@ -212,9 +218,15 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ kernels
     def _kernels(self, x, y, B):
+        cl = self.cluster if B * self.cluster <= 148 else 1
+        if self.fused_tail and B * cl <= 128:       # the tail's grid-wide check-in needs every CTA resident
+            tail = (self._grad_ptrs, self._inbox_ptrs, self.momentum, self.lr, self.mu, 1.0 / self.world, self.rank, self.world,
+                    self.ticket, None)
+            self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
+                                self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux, tail)
+            return
         self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
-                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride,
-                            self.cluster if B * self.cluster <= 148 else 1, self.aux)
+                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
                              self.done_counter, self.aux, self._inbox_ptrs)
@@ -332,7 +344,7 @@ class FusedTrainer:
             env = os.environ.get("B200DIST_EXEC_CHUNK")
             chunk = int(env) if env is not None else loader.num_buffers // 3
             chunk = max(1, min(8, chunk))
-            while chunk > 1 and (loader.num_buffers % chunk != 0 or loader.num_buffers < 3 * chunk):
+            while chunk > 1 and loader.num_buffers < 3 * chunk:
                 chunk -= 1
             in_dev = torch.zeros(max(2, 2 * chunk) * block, dtype=torch.uint8, device=self.device)
             loss_hist = torch.zeros(4 * max(1, chunk), dtype=torch.float32, device=self.device)
@@ -340,7 +352,8 @@ class FusedTrainer:
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
-                                      self.cluster, self.aux, chunk, self._inbox_ptrs, loss_hist),
+                                      self.cluster, self.aux, chunk, self._inbox_ptrs, loss_hist,
+                                      self.fused_tail and self.bsz * self.cluster <= 128, self.ticket),
                   self.training)
             self.exec_chunk = chunk
             self._executors[id(loader)] = ex

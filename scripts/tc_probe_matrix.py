@@ -144,6 +144,51 @@ for name, lbo, sbo in (("cute", atom, 256), ("swapped", 256, atom)):
     res[name] = float(np.abs(d.cpu().numpy() - ref).max() / np.abs(ref).max())
 out(**res)
 ''',
+
+    # ---- round 2, call 6: "shifted window" operands -- ONE image per tile in shared memory, the 25 taps are 25 descriptors
+    "umma_window_fwd_kmajor_sw32": '''
+rng = np.random.default_rng(6)
+pix = L.bf16_bits(rng.standard_normal((12, 2, 12, 16)).astype(np.float32))          # [y][b][x][c]: 32-byte pixels
+a_img = L.expected_tma_image_sw32(pix)
+b = L.bf16_bits(rng.standard_normal((32, 64)).astype(np.float32)); b_img = L.image_rows128(b)
+ky, kx = 2, 3
+ops = [L.smem_desc(ky * 768 + kx * 32, 16, 384, 6), L.smem_desc(0, 16, 1024, 2), 0, 0]
+d = C.umma_probe(torch.from_numpy(a_img).to(dev), torch.from_numpy(b_img).to(dev), L.idesc_bf16(128, 32), ops, 32).cpu().numpy()
+torch.cuda.synchronize()
+pf = L.bits_to_f32(pix); bf = L.bits_to_f32(b)[:, :16]
+ref = np.zeros((128, 32), np.float32)
+for oy in range(8):
+    for bb in range(2):
+        for ox in range(8):
+            ref[(oy * 2 + bb) * 8 + ox] = pf[oy + ky, bb, ox + kx] @ bf.T
+out(rel_err=float(np.abs(d - ref).max() / np.abs(ref).max()))
+''',
+    "umma_window_wgrad_mnmajor_sw32": '''
+rng = np.random.default_rng(7)
+pix = L.bf16_bits(rng.standard_normal((12, 12, 16)).astype(np.float32))             # one sample [y][x][c]
+a_img = np.concatenate([L.expected_tma_image_sw32(pix), np.zeros(1024, np.uint8)])
+b = L.bf16_bits(rng.standard_normal((32, 64)).astype(np.float32)); b_img = L.image_rows128(b)   # dC [co][pos]
+ky = 1
+ops = []
+for ks in range(4): ops += [L.smem_desc(ky * 384 + ks * 768, 32, 384, 6), L.smem_desc(ks * 32, 16, 1024, 2), 0, int(ks > 0)]
+d = C.umma_probe(torch.from_numpy(a_img).to(dev), torch.from_numpy(b_img).to(dev), L.idesc_bf16(128, 32, a_mn=1), ops, 32).cpu().numpy()
+torch.cuda.synchronize()
+pf = L.bits_to_f32(pix).reshape(144, 16); bf = L.bits_to_f32(b)
+ref = np.zeros((128, 32), np.float32)
+for kx in range(5):
+    for ci in range(16):
+        a_row = np.array([pf[(oy + ky) * 12 + ox + kx, ci] for oy in range(8) for ox in range(8)], np.float32)
+        ref[kx * 16 + ci] = bf @ a_row
+out(rel_err=float(np.abs(d[:80] - ref[:80]).max() / np.abs(ref[:80]).max()))
+''',
+    "tma4d_window_image_y_b_x_c": '''
+B = 5
+t = np.arange(B * 12 * 12 * 16, dtype=np.uint16).reshape(B, 12, 12, 16)
+# dims (c, x, b, y): box {16, 12, 2, 12} -> shared image [y][b][x][c]
+got = tma(t, [16, 12, B, 12], [32, 4608, 384], [16, 12, 2, 12], 1, [0, 0, 2, 0])
+want = L.expected_tma_image_sw32(np.ascontiguousarray(t[2:4].transpose(1, 0, 2, 3)))
+out(ok=bool(np.array_equal(got, want)))
+''',
     # ---- UMMA descriptor modes
     "umma_kmajor": '''
 rng = np.random.default_rng(0)

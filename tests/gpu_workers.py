@@ -168,10 +168,13 @@ def w_push_exchange_equals_barrier_exchange(rank, size):
     ds = D.SyntheticMNIST(n=bsz * size * 12 + 5 * size, seed=4)        # 12 full batches + a short tail per rank
     idx = list(range(rank, len(ds), size))
     results = {}
-    for push in ("0", "1"):
+    # (push, fused tail): barrier + peer loads in a second kernel | push in a second kernel | ONE kernel per step (default)
+    for push, fused in (("0", "1"), ("1", "0"), ("1", "1")):
         os.environ["B200DIST_SGD_PUSH"] = push
+        os.environ["B200DIST_FUSED_TAIL"] = fused
         tr = FusedTrainer(bsz, lr=0.05, seed=11, device=dev, p_drop=0.5, raw_uint8=True)
         assert (tr.inbox_handle is not None) == (push == "1")
+        assert tr.fused_tail == (push == "1" and fused == "1") and tr.gpu_launches_per_step == (1 if tr.fused_tail else 2)
         for i in range(7):                                             # python graph path, odd count -> both parities
             g = torch.Generator().manual_seed(50 + i * size + rank)
             tr.step(torch.randint(0, 255, (bsz, 1, 28, 28), generator=g, dtype=torch.uint8).pin_memory(),
@@ -185,17 +188,19 @@ def w_push_exchange_equals_barrier_exchange(rank, size):
         done, _ = tr.run_native(loader, max_steps=9)
         assert done == 9
         torch.cuda.synchronize()
-        results[push] = (tr.params.clone(), tr.momentum.clone(), int(tr.step_counter.item()))
+        results[push + fused] = (tr.params.clone(), tr.momentum.clone(), int(tr.step_counter.item()))
+        mine = tr.params.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other), ("replicas differ", push, fused)
         del tr
     os.environ.pop("B200DIST_SGD_PUSH", None)
-    assert results["0"][2] == results["1"][2] == 16
+    os.environ.pop("B200DIST_FUSED_TAIL", None)
+    assert results["01"][2] == results["10"][2] == results["11"][2] == 16
     # same maths in the same rank order; run-to-run differences only from the float-atomic gradient flush inside a GPU
-    assert torch.allclose(results["0"][0], results["1"][0], atol=2e-5, rtol=1e-4)
-    assert torch.allclose(results["0"][1], results["1"][1], atol=2e-5, rtol=1e-4)
-    mine = results["1"][0].clone()
-    other = mine.clone()
-    dist.broadcast(other, src=0)
-    assert torch.equal(mine, other)
+    for k in ("10", "11"):
+        assert torch.allclose(results["01"][0], results[k][0], atol=2e-5, rtol=1e-4), k
+        assert torch.allclose(results["01"][1], results[k][1], atol=2e-5, rtol=1e-4), k
     dist.barrier()
 
 
@@ -271,4 +276,166 @@ def w_train_torch_engine_gpu(rank, size):
     dist.broadcast(other, src=0)
     assert torch.equal(flat, other)
     ddp.remove_hooks()
+    dist.barrier()
+
+
+def w_suite_odd_world(rank, size):
+    """Everything that touches the peer-memory protocols, at a world size the power-of-two tests never see (the reference's
+    gloo.py:59 runs 7 ranks): all-reduce variants incl. sizes that are not multiples of the world, the fused trainer against
+    global-batch SGD, and the three exchange flavours against each other."""
+    dev = _dev()
+    w = symm.lookup_world(None)
+    assert w is not None and w.world == size
+    variants = [0, 1] + ([2] if w.multicast else [])
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        for n in (1, 5, 64, 21888, 65536 + 3, (1 << 20) + 7):
+            g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+            local = torch.randn(n, generator=g).to(dev).to(dtype)
+            ref = local.clone().float()
+            dist.all_reduce(ref)
+            ref = ref / size
+            hd = w.alloc(n, dtype)
+            for v in variants:
+                hd.local.zero_()
+                hd.local[:n].copy_(local)
+                torch.cuda.synchronize()
+                dist.barrier()
+                w.all_reduce_(hd.local, scale=1.0 / size, handle=hd, variant=v)
+                torch.cuda.synchronize()
+                got = hd.local[:n].float()
+                assert torch.allclose(got, ref, atol=tol, rtol=tol), (size, str(dtype), n, v, float((got - ref).abs().max()))
+                mine = hd.local[:n].clone()
+                other = mine.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(mine, other), ("replica mismatch", size, str(dtype), n, v)
+            t = local.clone()
+            w.all_reduce_(t, scale=1.0 / size)
+            torch.cuda.synchronize()
+            assert torch.allclose(t.float(), ref, atol=tol, rtol=tol), ("staged", size, str(dtype), n)
+    w_fused_trainer(rank, size)
+    w_push_exchange_equals_barrier_exchange(rank, size)
+
+
+def w_flag_reuse_stress(rank, size):
+    """10^5 back-to-back fused all-reduces with the variant changing every call (signal-pad epochs, SURVEY 7.4 hard part 1),
+    then 20000 one-kernel training steps replayed from CUDA graphs (inbox epochs / parity double-buffer of the push exchange)."""
+    dev = _dev()
+    w = symm.lookup_world(None)
+    variants = [0, 1] + ([2] if w.multicast else [])
+    hd = w.alloc(4096, torch.float32)
+    n_it = int(os.environ.get("B200DIST_STRESS_ITERS", "100000"))
+    hd.local.fill_(1.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    for it in range(n_it):                       # t <- mean over ranks of t  (stays exactly 1.0: any lost/duplicated add shows)
+        w.all_reduce_(hd.local, scale=1.0 / size, handle=hd, variant=variants[it % len(variants)])
+        if it % 10000 == 9999:
+            torch.cuda.synchronize()
+            assert torch.allclose(hd.local, torch.ones_like(hd.local), atol=1e-4), (it, float(hd.local.min()), float(hd.local.max()))
+    torch.cuda.synchronize()
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    bsz = max(1, 128 // size)
+    tr = FusedTrainer(bsz, lr=0.001, seed=3, device=dev, p_drop=0.5)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    xs = torch.randn(8, bsz, 1, 28, 28, device=dev, generator=g)
+    ys = torch.randint(0, 10, (8, bsz), device=dev, generator=g)
+    st = tr.stream
+    with torch.cuda.stream(st):
+        tr._kernels(xs[0], ys[0], bsz)
+    st.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=st):
+        for i in range(8):
+            tr._kernels(xs[i], ys[i], bsz)
+    with torch.cuda.stream(st):
+        for _ in range(2500):
+            gr.replay()
+    st.synchronize()
+    assert int(tr.step_counter.item()) == 20001
+    assert bool(torch.isfinite(tr.params).all())
+    mine = tr.params.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other)
+    dist.barrier()
+
+
+def w_large_sizes_vs_nccl(rank, size):
+    """Full-tensor comparison against NCCL up to 1 GiB (BASELINE B3 range), every variant the host exposes."""
+    dev = _dev()
+    w = symm.lookup_world(None)
+    variants = [1] + ([2] if w.multicast else [])
+    for n in (16 << 20, 64 << 20, 256 << 20):            # fp32 elements: 64 MiB, 256 MiB, 1 GiB
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        hd = w.alloc(n, torch.float32)
+        src = torch.randn(n, device=dev, generator=g)
+        ref = src.clone()
+        dist.all_reduce(ref)
+        for v in variants:
+            hd.local[:n].copy_(src)
+            torch.cuda.synchronize()
+            dist.barrier()
+            w.all_reduce_(hd.local, handle=hd, variant=v)
+            torch.cuda.synchronize()
+            err = float((hd.local[:n] - ref).abs().max())
+            assert err < 1e-3, (n, v, err)
+        del src, ref
+    dist.barrier()
+
+
+def w_subgroup_symmetric_world(rank, size):
+    """tuto.md:176-186: collectives on a sub-group.  A symmetric world (own mappings, own signal pads) over a subset of
+    the GPUs, used by all_reduce and by a fused trainer, while the other ranks idle."""
+    dev = _dev()
+    members = list(range(1, size)) if size > 2 else [0, 1]
+    grp = b2.new_group(members)
+    if rank in members:
+        t = torch.full((1000,), float(rank + 1), device=dev)
+        b2.all_reduce(t, group=grp)
+        assert float(t[0]) == float(sum(r + 1 for r in members))
+        wg = symm.lookup_world(grp) or symm.init_world(grp)
+        assert wg.world == len(members)
+        from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+        tr = FusedTrainer(8, seed=2, device=dev, p_drop=0.5, group=grp)
+        for i in range(6):
+            g = torch.Generator().manual_seed(40 + i * size + rank)
+            tr.step(torch.randn(8, 1, 28, 28, generator=g).pin_memory(), torch.randint(0, 10, (8,), generator=g).pin_memory())
+        tr.sync_lag(0)
+        torch.cuda.synchronize()
+        mine = tr.params.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=members[0], group=grp)
+        assert torch.equal(mine, other)
+    dist.barrier()
+
+
+def w_batched_trainer(rank, size):
+    """Batched tensor-core engine, world N == torch SGD on the concatenated global batch (eval-mode network)."""
+    dev = _dev()
+    from dist_tuto.pth_b200.models.convnet import Net
+    from dist_tuto.pth_b200.ops.convnet_batched import BatchedTrainer
+    from dist_tuto.pth_b200.ops.convnet_fused import unpack_params
+    bsz = 192
+    torch.manual_seed(33)
+    ref = Net(p_drop=0.0).to(dev).eval()
+    tr = BatchedTrainer(bsz, lr=0.05, momentum=0.5, seed=21, device=dev, p_drop=0.0, init_from=ref)
+    tr.eval()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.5)
+    for i in range(6):
+        g = torch.Generator().manual_seed(500 + i)
+        xg = torch.randn(bsz * size, 1, 28, 28, generator=g)
+        yg = torch.randint(0, 10, (bsz * size,), generator=g)
+        tr.step(xg[rank * bsz:(rank + 1) * bsz].contiguous().pin_memory(), yg[rank * bsz:(rank + 1) * bsz].contiguous().pin_memory())
+        opt.zero_grad()
+        F.nll_loss(ref(xg.to(dev)), yg.to(dev)).backward()
+        opt.step()
+    tr.stream.synchronize()
+    views = unpack_params(tr.params)
+    for name, p in ref.named_parameters():
+        rel = float((views[name] - p.detach()).norm() / p.detach().norm())
+        assert rel < 2e-2, (name, rel)
+    mine = tr.params.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other)
     dist.barrier()

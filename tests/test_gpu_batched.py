@@ -48,17 +48,20 @@ def _case(B, seed, training):
 @pytest.mark.parametrize("B,training", [(2, False), (64, True), (333, True)])
 def test_every_stage_matches_the_rounding_exact_model(B, training):
     params, x, y, step, m2, dm = _case(B, 11 + B, training)
-    ref = R.forward_backward(params, x, y, m2, dm, emulate_bf16=True)
+    ref0 = R.forward_backward(params, x, y, m2, dm, emulate_bf16=True)
     loss, grads, bufs = batched_loss_and_grads(params, x, y, training=training, seed=77, step=step)
     torch.cuda.synchronize()
     rep = {"B": B, "training": training}
-    p1 = bufs.P1.view(B, 16, 12, 16)[:, :10, :, :12].float()
-    rep["p1"] = _rel(p1, ref["p1"])
-    rep["p1_ones_channel_intact"] = bool((bufs.P1.view(B, 16, 12, 16)[:, 10, :, :12] == 1).all())
-    a1 = (bufs.A1.view(B, 10, 12, 12) & 3).long()
-    ref_a1 = ref["a1"]                                  # flat index into the 24x24 map
-    ry, rx = (ref_a1 // 24) % 2, (ref_a1 % 24) % 2
-    rep["a1_agree"] = float(((a1 == ry * 2 + rx) | (ref["p1"] == 0)).float().mean())
+    p1 = bufs.P1.view(B, 12, 12, 16)[..., :10].permute(0, 3, 1, 2).float()
+    rep["p1_vs_torch_conv"] = _rel(p1, ref0["p1"])                 # different fp32 summation order: a few bf16 ulps
+    rep["p1_ones_channel_intact"] = bool((bufs.P1.view(B, 12, 12, 16)[..., 10] == 1).all() and (bufs.P1.view(B, 12, 12, 16)[..., 11:] == 0).all())
+    code = bufs.A1.view(B, 10, 12, 12)
+    a1 = (code & 3).long()
+    ry, rx = (ref0["a1"] // 24) % 2, (ref0["a1"] % 24) % 2
+    rep["a1_agree"] = float(((a1 == ry * 2 + rx) | (ref0["p1"] == 0)).float().mean())
+    rep["a1_dead_flag"] = float((((code & 4) != 0) == (p1 == 0)).float().mean())
+    # everything downstream is compared on the engine's own (bit-identical) conv1 output
+    ref = R.forward_backward(params, x, y, m2, dm, emulate_bf16=True, p1_override=p1, a1_override=a1)
     rep["p2"] = _rel(bufs.P2.view(B, 320), ref["p2"])
     rep["hrelu"] = _rel(bufs.Hrelu.view(B, 64)[:, :50], ref["hrelu"])
     rep["loss"] = abs(float(loss) - float(ref["loss"])) / abs(float(ref["loss"]))
@@ -70,9 +73,11 @@ def test_every_stage_matches_the_rounding_exact_model(B, training):
     for n in want:
         rep["grad/" + n] = _rel(mine[n], want[n])
     _dump(f"batched_diag_B{B}.json", rep)
-    bad = {k: v for k, v in rep.items() if isinstance(v, float) and k != "a1_agree" and v > 5e-3}
+    loose = ("a1_agree", "a1_dead_flag", "p1_vs_torch_conv")
+    bad = {k: v for k, v in rep.items() if isinstance(v, float) and k not in loose and v > 5e-3}
     assert not bad, rep
-    assert rep["a1_agree"] > 0.999 and rep["p1_ones_channel_intact"] and rep["dc_pad_zero"], rep
+    assert rep["a1_agree"] > 0.999 and rep["a1_dead_flag"] == 1.0 and rep["p1_vs_torch_conv"] < 5e-3, rep
+    assert rep["p1_ones_channel_intact"] and rep["dc_pad_zero"], rep
 
 
 def test_forward_only_matches_net_eval():

@@ -43,3 +43,27 @@ def test_push_exchange_equals_barrier_exchange():
 
 def test_train_loop_torch_engine_symmetric_bucket_and_flat_sgd():
     go(W.w_train_torch_engine_gpu)
+
+
+def test_batched_tensor_core_trainer_equals_global_batch_sgd():
+    go(W.w_batched_trainer)
+
+
+def test_subgroup_symmetric_world():
+    go(W.w_subgroup_symmetric_world, size=max(2, min(_n(), 4)))
+
+
+@pytest.mark.parametrize("world", [3, 5, 6, 7])
+def test_odd_worlds(world):
+    """gloo.py:59 runs 7 ranks; two-shot / NVLS slicing and the inbox layout must not assume a power of two."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    go(W.w_suite_odd_world, size=world)
+
+
+def test_flag_reuse_stress_1e5():
+    go(W.w_flag_reuse_stress)
+
+
+def test_large_messages_vs_nccl_to_1gib():
+    go(W.w_large_sizes_vs_nccl)
