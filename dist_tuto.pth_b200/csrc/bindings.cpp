@@ -52,12 +52,14 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const void* tail, cudaStream_t stream);
+                           const void* tail, float* det_partials, cudaStream_t stream);
+int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stride, float* grads, const unsigned long long* step,
+                         long long grad_stride, size_t n_elems, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const void* tail, cudaStream_t stream);
+                              const float* aux, const void* tail, float* det_partials, cudaStream_t stream);
 void b2_convnet_set_tc(int on);
 int b2_convnet_get_tc();
 int b2_gemm_available();
@@ -320,7 +322,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                            c10::optional<torch::Tensor> loss_acc, c10::optional<torch::Tensor> out_logp,
                            c10::optional<torch::Tensor> mask_out, c10::optional<torch::Tensor> step, uint64_t seed,
                            int64_t sample_base, bool training, double inv_bsz, double p_drop, int max_ctas, int64_t grad_stride, int cluster,
-                           c10::optional<torch::Tensor> aux, py::object tail) {
+                           c10::optional<torch::Tensor> aux, py::object tail, c10::optional<torch::Tensor> det_partials) {
     check_cuda_contig(params, "params"); check_cuda_contig(x, "x"); check_cuda_contig(target, "target");
     TORCH_CHECK(params.scalar_type() == torch::kFloat32 && params.numel() >= b2_convnet_npar(), "params: flat fp32 [21848]");
     TORCH_CHECK(target.scalar_type() == torch::kInt64, "target: int64");
@@ -367,20 +369,36 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       th.lr = t[3].cast<float>(); th.mu = t[4].cast<float>(); th.scale = t[5].cast<float>();
       tp = &th;
     }
+    float* dp = nullptr;
+    if (det_partials.has_value()) {
+      TORCH_CHECK(tp == nullptr, "deterministic mode and the fused tail are mutually exclusive");
+      TORCH_CHECK(det_partials->is_cuda() && det_partials->scalar_type() == torch::kFloat32 &&
+                  det_partials->numel() >= (int64_t)std::max(1, B * std::max(1, cluster)) * 21888, "det_partials: [ctas, 21888] fp32");
+      dp = det_partials->data_ptr<float>();
+    }
     if (cluster > 1) {
       TORCH_CHECK(cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 1, 2, 4 or 8");
       ck_cuda(b2_convnet_cluster_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                         la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                        cluster, max_ctas, grad_stride, ax, tp, cur_stream()), "convnet_cluster launch");
+                                        cluster, max_ctas, grad_stride, ax, tp, dp, cur_stream()), "convnet_cluster launch");
       return;
     }
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                   max_ctas, grad_stride, ax, tp, cur_stream()), "convnet_step launch");
+                                   max_ctas, grad_stride, ax, tp, dp, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
      py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none(),
-     py::arg("tail") = py::none());
+     py::arg("tail") = py::none(), py::arg("det_partials") = py::none());
+  m.def("det_reduce", [](torch::Tensor partials, int n_slots, torch::Tensor grads, c10::optional<torch::Tensor> step, int64_t grad_stride) {
+    // deterministic mode: grads[(step & 1) * grad_stride ...] = sum over the first n_slots per-CTA slots, in slot order
+    check_cuda_contig(partials, "partials"); check_cuda_contig(grads, "grads");
+    TORCH_CHECK(partials.scalar_type() == torch::kFloat32 && grads.scalar_type() == torch::kFloat32 && partials.numel() >= (int64_t)n_slots * 21888);
+    const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
+    c10::cuda::CUDAGuard guard(grads.device());
+    ck_cuda(b2_det_reduce_launch(partials.data_ptr<float>(), n_slots, 21888, grads.data_ptr<float>(), st, grad_stride,
+                                 (size_t)b2_convnet_npar(), cur_stream()), "det_reduce launch");
+  }, py::arg("partials"), py::arg("n_slots"), py::arg("grads"), py::arg("step") = py::none(), py::arg("grad_stride") = 0);
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });

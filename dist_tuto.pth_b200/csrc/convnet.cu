@@ -707,10 +707,15 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 
   // ------------------------------------------------------------------ flush
   if (a.backward && blockIdx.x < a.B) {
-    float* gdst = a.grads + (size_t)(step & 1ull) * (size_t)a.grad_stride;   // double-buffered buckets: see sgd.cu
-    for (int v = tid; v < NPAR / 4; v += T) {
-      const float4 q = *reinterpret_cast<const float4*>(&s.g[v * 4]);
-      red_add_v4(gdst + v * 4, q.x, q.y, q.z, q.w);
+    if (a.det_partials != nullptr) {        // deterministic mode: a private slot per CTA, summed in CTA order afterwards
+      float4* slot = reinterpret_cast<float4*>(a.det_partials + (size_t)blockIdx.x * DET_STRIDE);
+      for (int v = tid; v < NPAR / 4; v += T) slot[v] = *reinterpret_cast<const float4*>(&s.g[v * 4]);
+    } else {
+      float* gdst = a.grads + (size_t)(step & 1ull) * (size_t)a.grad_stride;   // double-buffered buckets: see sgd.cu
+      for (int v = tid; v < NPAR / 4; v += T) {
+        const float4 q = *reinterpret_cast<const float4*>(&s.g[v * 4]);
+        red_add_v4(gdst + v * 4, q.x, q.y, q.z, q.w);
+      }
     }
   }
   if (tid == 0 && a.loss_acc != nullptr && blockIdx.x < a.B) {
@@ -747,7 +752,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const cn::FusedTailHost* tail, cudaStream_t stream) {
+                           const cn::FusedTailHost* tail, float* det_partials, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cn::Smem) + 1024;
   if (!configured) {
@@ -763,6 +768,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
   a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
   cn::fill_tail(a.tail, backward ? tail : nullptr, grad_stride);
+  a.det_partials = backward ? det_partials : nullptr;
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;

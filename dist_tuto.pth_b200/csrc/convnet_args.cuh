@@ -36,7 +36,10 @@ struct Args {
   long long grad_stride;    // elements between the two gradient buckets (0: single bucket); bucket = step & 1
   const float* aux;         // optional: conv2.weight pre-arranged by the SGD kernel as [w2f 5000 | w2b 8000] (see sgd.cu)
   b2::FusedTail tail;       // enabled: gradient exchange + SGD run in the tail of THIS kernel (sgd_device.cuh)
+  float* det_partials;      // deterministic mode: CTA i stores its gradient sums to det_partials + i * DET_STRIDE (plain
+                            // stores) instead of red.add-ing into the bucket; det_reduce_kernel (sgd.cu) sums the slots in order
 };
+constexpr int DET_STRIDE = 21888;   // = NPAR_ALLOC of ops/convnet_fused.py
 
 // Host-side description of the fused tail (C ABI of the launchers); nullptr / enabled == 0 -> two-kernel step.
 struct FusedTailHost {

@@ -499,7 +499,12 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
   // ------------------------------------------------------------------ flush: only the gradient slices this CTA owns
   if (a.backward && cluster_id < a.B) {
     float* gdst = a.grads + (size_t)(step & 1ull) * (size_t)a.grad_stride;
+    if (a.det_partials != nullptr) {               // deterministic mode: whole private slot per CTA (zeros outside its slices)
+      float4* slot = reinterpret_cast<float4*>(a.det_partials + (size_t)blockIdx.x * DET_STRIDE);
+      for (int v = tid; v < NPAR / 4; v += T) slot[v] = *reinterpret_cast<const float4*>(&s.g[v * 4]);
+    }
     auto flush = [&](int lo, int hi) {             // element range, widened to whole float4 (other CTAs hold zeros there)
+      if (a.det_partials != nullptr) return;
       lo &= ~3;
       hi = (hi + 3) & ~3;
       if (hi > NPAR) hi = NPAR;
@@ -534,7 +539,7 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const cn::FusedTailHost* tail, cudaStream_t stream) {
+                              const float* aux, const cn::FusedTailHost* tail, float* det_partials, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cnc::Smem);
   if (!configured) {
@@ -550,6 +555,7 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
   a.training = training; a.backward = backward; a.inv_bsz = inv_bsz; a.p_drop = p_drop;
   a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
   cn::fill_tail(a.tail, backward ? tail : nullptr, grad_stride);
+  a.det_partials = backward ? det_partials : nullptr;
   int clusters = B;
   if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
   if (clusters < 1) clusters = 1;

@@ -24,7 +24,9 @@
 // memory and its own D2H read-back; the per-step path remains for the steps that do not fill a chunk.
 #include "executor.h"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 extern "C" {
@@ -32,7 +34,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const void* tail, cudaStream_t stream);
+                           const void* tail, float* det_partials, cudaStream_t stream);
 struct PeerPtrsC { void* p[8]; };
 struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
@@ -43,7 +45,7 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const void* tail, cudaStream_t stream);
+                              const float* aux, const void* tail, float* det_partials, cudaStream_t stream);
 int b2_convnet_npar();
 struct FusedTailHostC {            // mirrors cn::FusedTailHost (csrc/convnet_args.cuh)
   void* grad_ptrs[8];
@@ -74,6 +76,11 @@ StepExecutor::StepExecutor(const StepConfig& cfg, NativeLoader* loader, int max_
   for (int p = 0; p < 2; ++p) {
     cudaEventCreateWithFlags(&copied_[p], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&kernels_done_[p], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&loss_read_[p], cudaEventDisableTiming);
+  }
+  {
+    const char* e = getenv("B200DIST_EXEC_DIRECT");
+    direct_ = (e == nullptr || e[0] != '0');
   }
   const int K = cfg_.chunk, nb = loader_->num_slots();
   chunk_ok_ = K >= 2 && K <= 8 && nb >= 3 * K && cfg_.loss_hist != nullptr;
@@ -83,8 +90,9 @@ StepExecutor::StepExecutor(const StepConfig& cfg, NativeLoader* loader, int max_
       cudaEventCreateWithFlags(&comp_done_[g], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&d2h_done_[g], cudaEventDisableTiming);
     }
-    copy_ev_.resize(nb / K + 2);
+    copy_ev_.resize(nb + 2);
     for (auto& e : copy_ev_) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (int k = K; k >= 1 && n_sizes_ < 4; k /= 2) chunk_sizes_[n_sizes_++] = k;
   }
   slots_.resize(loader_->num_slots());
   for (auto& s : slots_) {
@@ -103,7 +111,7 @@ StepExecutor::~StepExecutor() {
   }
   for (auto e : copy_ev_) if (e) cudaEventDestroy(e);
   for (int g = 0; g < 2; ++g) {
-    if (comp_exec_[g]) cudaGraphExecDestroy(comp_exec_[g]);
+    for (int i = 0; i < 4; ++i) if (comp_exec_[g][i]) cudaGraphExecDestroy(comp_exec_[g][i]);
     if (h2d_done_[g]) cudaEventDestroy(h2d_done_[g]);
     if (comp_done_[g]) cudaEventDestroy(comp_done_[g]);
     if (d2h_done_[g]) cudaEventDestroy(d2h_done_[g]);
@@ -112,6 +120,7 @@ StepExecutor::~StepExecutor() {
     if (exec_[p]) cudaGraphExecDestroy(exec_[p]);
     if (copied_[p]) cudaEventDestroy(copied_[p]);
     if (kernels_done_[p]) cudaEventDestroy(kernels_done_[p]);
+    if (loss_read_[p]) cudaEventDestroy(loss_read_[p]);
   }
   if (copy_) cudaStreamDestroy(copy_);
   if (compute_) cudaStreamDestroy(compute_);
@@ -134,10 +143,10 @@ void StepExecutor::record_step(const void* x, const long long* y, float* loss_sn
   int rc = cfg_.cluster > 1
                ? b2_convnet_cluster_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                            cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1,
-                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, tp, compute_)
+                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, compute_)
                : b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                         cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
-                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, tp, compute_);
+                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, compute_);
   int rc2 = 0;
   if (!cfg_.fused_tail) {
     PeerPtrsC g;
@@ -159,7 +168,8 @@ bool StepExecutor::capture(int parity) {
   cudaError_t e = cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
   err_.clear();
-  record_step(cfg_.in_dev[parity], reinterpret_cast<const long long*>(cfg_.in_dev[parity] + loader_->y_offset()));
+  record_step(cfg_.in_dev[parity], reinterpret_cast<const long long*>(cfg_.in_dev[parity] + loader_->y_offset()),
+              cfg_.loss_hist != nullptr ? cfg_.loss_hist + 2 * parity : nullptr);
   e = cudaStreamEndCapture(compute_, &graph);
   if (!err_.empty() || e != cudaSuccess || graph == nullptr) {
     if (err_.empty()) err_ = std::string("graph capture failed: ") + cudaGetErrorString(e);
@@ -188,26 +198,28 @@ static bool end_capture(cudaStream_t st, cudaGraphExec_t* out, std::string* err,
   return true;
 }
 
-bool StepExecutor::capture_chunk(int g) {
-  const int K = cfg_.chunk;
+bool StepExecutor::capture_chunk(int g, int si) {
+  const int K = cfg_.chunk, k = chunk_sizes_[si];
   err_.clear();
-  if (comp_exec_[g] != nullptr) return true;           // K steps' kernels: a pure chain, PDL intact from step to step
+  if (comp_exec_[g][si] != nullptr) return true;       // k steps' kernels: a pure chain, PDL intact from step to step
   cudaError_t e = cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { err_ = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); return false; }
-  for (int j = 0; j < K; ++j) {
+  for (int j = 0; j < k; ++j) {
     unsigned char* blk = cfg_.in_dev[g * K + j];
     record_step(blk, reinterpret_cast<const long long*>(blk + loader_->y_offset()), cfg_.loss_hist + 2 * (g * K + j));
   }
-  return end_capture(compute_, &comp_exec_[g], &err_, "compute chunk");
+  return end_capture(compute_, &comp_exec_[g][si], &err_, "compute chunk");
 }
 
 // Captures (and instantiates) every graph the hot loop replays, so that no capture lands inside a timed / training region.
 bool StepExecutor::prepare() {
-  for (int p = 0; p < 2; ++p)
-    if (exec_[p] == nullptr && !capture(p)) return false;
+  if (!direct_)
+    for (int p = 0; p < 2; ++p)
+      if (exec_[p] == nullptr && !capture(p)) return false;
   if (chunk_ok_)
-    for (int g = 0; g < 2; ++g)
-      if (!capture_chunk(g)) { chunk_ok_ = false; chunk_note_ = err_; err_.clear(); break; }
+    for (int g = 0; g < 2 && chunk_ok_; ++g)
+      for (int si = 0; si < n_sizes_; ++si)
+        if (!capture_chunk(g, si)) { chunk_ok_ = false; chunk_note_ = err_; err_.clear(); break; }
   return true;
 }
 
@@ -256,10 +268,15 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
   const int K = cfg_.chunk, nb = loader_->num_slots();
   struct Total { long long t0; Stats* s; ~Total() { s->total_ns += now_ns() - t0; } } total{now_ns(), &stats_};
   while (max_steps < 0 || done < max_steps) {
-    // ---- chunk path: K full batches ahead and the budget allows
-    if (chunk_ok_ && (max_steps < 0 || max_steps - done >= K) && loader_->full_batches_left() >= K) {
+    // ---- chunk path: the largest chunk size (K, K/2, ...) that the budget and the epoch's full batches allow
+    const int64_t room = std::min<int64_t>(max_steps < 0 ? K : max_steps - done, loader_->full_batches_left());
+    int si = -1;
+    for (int i = 0; i < n_sizes_; ++i)
+      if (chunk_sizes_[i] <= room) { si = i; break; }
+    if (chunk_ok_ && si >= 0) {
+      const int kc = chunk_sizes_[si];
       const int g = (int)(chunks_issued_ & 1);
-      if (comp_exec_[g] == nullptr && !capture_chunk(g)) {
+      if (comp_exec_[g][si] == nullptr && !capture_chunk(g, si)) {
         chunk_ok_ = false;
         chunk_note_ = err_;
         err_.clear();
@@ -274,7 +291,7 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
       cudaStreamWaitEvent(copy_, kernels_done_[0], 0);
       cudaStreamWaitEvent(copy_, kernels_done_[1], 0);
       int slot_of[8];
-      for (int j = 0; j < K; ++j) {                                 // blocks until batch j is staged
+      for (int j = 0; j < kc; ++j) {                                // blocks until batch j is staged
         int64_t count = 0;
         const long long tn = now_ns();
         const int slot = loader_->next(&count);
@@ -286,26 +303,26 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
       const int ev = (int)(chunks_issued_ % (int64_t)copy_ev_.size());
       cudaEventRecord(copy_ev_[ev], copy_);
       cudaEventRecord(h2d_done_[g], copy_);
-      copy_q_.push_back({ev, K});
-      held_ += K;
+      copy_q_.push_back({ev, kc});
+      held_ += kc;
       // kernels: after the copies, and after the losses of the chunk that last used snapshot group g have been read back
       cudaStreamWaitEvent(compute_, h2d_done_[g], 0);
       cudaStreamWaitEvent(compute_, d2h_done_[g], 0);
-      cudaError_t e = cudaGraphLaunch(comp_exec_[g], compute_);
+      cudaError_t e = cudaGraphLaunch(comp_exec_[g][si], compute_);
       if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch(compute chunk): ") + cudaGetErrorString(e); return -1; }
       cudaEventRecord(comp_done_[g], compute_);
       if (g == 0) { cudaEventRecord(kernels_done_[0], compute_); cudaEventRecord(kernels_done_[1], compute_); }
       // losses
       cudaStreamWaitEvent(d2h_, comp_done_[g], 0);
-      for (int j = 0; j < K; ++j)
+      for (int j = 0; j < kc; ++j)
         cudaMemcpyAsync(slots_[slot_of[j]].loss_pin, cfg_.loss_hist + 2 * (g * K + j), 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
       cudaEventRecord(d2h_done_[g], d2h_);
-      cudaEventRecord(slots_[slot_of[K - 1]].done, d2h_);
-      for (int j = 0; j < K; ++j) in_flight_.push_back({slot_of[j], slot_of[K - 1], true});
+      cudaEventRecord(slots_[slot_of[kc - 1]].done, d2h_);
+      for (int j = 0; j < kc; ++j) in_flight_.push_back({slot_of[j], slot_of[kc - 1], true});
       ++chunks_issued_;
-      issued_ += K;
-      done += K;
-      stats_.chunk_steps += K;
+      issued_ += kc;
+      done += kc;
+      stats_.chunk_steps += kc;
       continue;
     }
     drain_copies();                                                 // per-step path below releases at retire: keep the order
@@ -323,20 +340,31 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
       break;
     }
     const int p = (int)(issued_ & 1);
-    if (exec_[p] == nullptr && !capture(p)) return -1;
+    if (!direct_ && exec_[p] == nullptr && !capture(p)) return -1;
     // H2D: block[p] is free once the kernels that last read it (two steps ago, or a chunk of group 0) are done
     cudaStreamWaitEvent(copy_, kernels_done_[p], 0);
     cudaMemcpyAsync(cfg_.in_dev[p], loader_->slot(slot).x, loader_->block_bytes(), cudaMemcpyHostToDevice, copy_);
     cudaEventRecord(copied_[p], copy_);
-    // kernels
+    // kernels.  direct mode (default): plain stream launches with the programmatic-dependent-launch attribute -- the steps
+    // chain on the device exactly as inside one long graph (a graph launch per step costs ~3 us of device time at every
+    // boundary: 31 vs 28 us per step, profiles/e2e_executor.json); graph mode: one 2-kernel graph per step.
     cudaStreamWaitEvent(compute_, copied_[p], 0);
-    cudaError_t e = cudaGraphLaunch(exec_[p], compute_);
-    if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); return -1; }
+    float* snap = cfg_.loss_hist != nullptr ? cfg_.loss_hist + 2 * p : nullptr;
+    if (snap != nullptr) cudaStreamWaitEvent(compute_, loss_read_[p], 0);   // snapshot slot p was read back (two steps ago)
+    if (direct_) {
+      err_.clear();
+      record_step(cfg_.in_dev[p], reinterpret_cast<const long long*>(cfg_.in_dev[p] + loader_->y_offset()), snap);
+      if (!err_.empty()) return -1;
+    } else {
+      cudaError_t e = cudaGraphLaunch(exec_[p], compute_);
+      if (e != cudaSuccess) { err_ = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); return -1; }
+    }
     cudaEventRecord(kernels_done_[p], compute_);
-    // loss read-back
+    // loss read-back: the cumulative loss as of THIS step (snapshotted on the device by the step's optimizer kernel)
     cudaStreamWaitEvent(d2h_, kernels_done_[p], 0);
-    cudaMemcpyAsync(slots_[slot].loss_pin, cfg_.loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
+    cudaMemcpyAsync(slots_[slot].loss_pin, snap != nullptr ? snap : cfg_.loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
     cudaEventRecord(slots_[slot].done, d2h_);
+    if (snap != nullptr) cudaEventRecord(loss_read_[p], d2h_);
     in_flight_.push_back({slot, slot, false});
     ++issued_;
     ++done;

@@ -61,7 +61,7 @@ class StepExecutor {
     float* loss_pin = nullptr;
   };
   bool capture(int parity);
-  bool capture_chunk(int g);
+  bool capture_chunk(int g, int size_idx);
   void release_copied(bool block_for_one);
   void drain_copies();
   void record_step(const void* x, const long long* y, float* loss_snapshot = nullptr);
@@ -71,11 +71,16 @@ class StepExecutor {
   int max_in_flight_;
   cudaStream_t copy_ = nullptr, compute_ = nullptr, d2h_ = nullptr;
   cudaGraphExec_t exec_[2] = {nullptr, nullptr};     // the two kernels, reading in_dev[parity]
-  cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr};
+  cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr}, loss_read_[2] = {nullptr, nullptr};
+  bool direct_ = true;                               // per-step path: plain PDL stream launches instead of a graph per step
   std::vector<Slot> slots_;
   // chunk pipeline: K consecutive steps = three graph launches on three streams (see executor.cpp).  The slot of batch b is
   // b % num_slots, so the pinned addresses of a slot group are fixed; g = chunk parity selects the device block group.
-  cudaGraphExec_t comp_exec_[2] = {nullptr, nullptr};  // the K steps' kernels reading device block group g
+  // kernels of k consecutive steps reading device blocks g*K .. g*K+k-1, for k = K, K/2, K/4, ... (index 0..3): a run of n
+  // steps is issued as chunks of decreasing size, so only a short tail BATCH ever takes the per-step path
+  cudaGraphExec_t comp_exec_[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  int chunk_sizes_[4] = {0, 0, 0, 0};
+  int n_sizes_ = 0;
   std::vector<cudaEvent_t> copy_ev_;                   // "H2D copies of chunk c are done" (ring)
   struct CopyFlight { int ev, count; };
   std::deque<CopyFlight> copy_q_;                      // chunks whose loader slots are still held

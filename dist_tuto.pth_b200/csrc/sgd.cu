@@ -105,6 +105,25 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs
   if (threadIdx.x == 0 && seen == gridDim.x - 1) { *a.done_counter = 0u; *a.step = st + 1ull; }
 }
 
+// Deterministic mode of the fused ConvNet step (convnet_args.cuh: det_partials): every step CTA stored its gradient sums to a
+// private slot; this kernel adds the slots IN CTA ORDER into this step's bucket, so the local sum -- and with the fixed rank
+// order of the exchange the whole update -- is bit-reproducible from run to run (float red.add into one bucket is not).
+__global__ void __launch_bounds__(256) det_reduce_kernel(const float* __restrict__ partials, int n_slots, long long slot_stride,
+                                                         float* __restrict__ grads, const unsigned long long* __restrict__ step,
+                                                         long long grad_stride, int n_vec) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= n_vec) return;
+  const unsigned long long st = step != nullptr ? *step : 0ull;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sl = 0; sl < n_slots; ++sl) {
+    const float4 q = __ldcg(reinterpret_cast<const float4*>(partials + (size_t)sl * slot_stride) + v);
+    acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+  }
+  reinterpret_cast<float4*>(grads + (size_t)(st & 1ull) * (size_t)grad_stride)[v] = acc;
+}
+
 // Plain flat momentum SGD (generic models: gradients already averaged in `grad`)
 __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ m,
                                                        const float* __restrict__ g, size_t n, float lr, float mu,
@@ -169,6 +188,22 @@ int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, fl
   cfg.numAttrs = pdl ? 1 : 0;
   return push ? (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_push_kernel, a)
               : (int)cudaLaunchKernelEx(&cfg, b2::allreduce_sgd_kernel, a);
+}
+
+int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stride, float* grads, const unsigned long long* step,
+                         long long grad_stride, size_t n_elems, cudaStream_t stream) {
+  const int n_vec = (int)(n_elems / 4);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((n_vec + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, b2::det_reduce_kernel, partials, n_slots, slot_stride, grads, step, grad_stride, n_vec);
 }
 
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,

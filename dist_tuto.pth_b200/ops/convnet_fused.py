@@ -118,7 +118,8 @@ class FusedTrainer:
 
     def __init__(self, bsz: int, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234, device=None,
                  p_drop: float = 0.5, group=None, raw_uint8: bool = False, num_slots: int = 4,
-                 use_graph: bool = True, init_from: Optional[Net] = None, cluster: Optional[int] = None):
+                 use_graph: bool = True, init_from: Optional[Net] = None, cluster: Optional[int] = None,
+                 deterministic: bool = False):
         self.C = _ext.C()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.bsz, self.lr, self.mu, self.seed, self.p_drop = int(bsz), float(lr), float(momentum), int(seed), p_drop
@@ -185,7 +186,17 @@ class FusedTrainer:
         self._last_loss_cum = 0.0
         # "one kernel per step": gradient exchange + SGD run in the tail of the step kernel (csrc/sgd_device.cuh: grid-wide
         # check-in, then every CTA pushes / reduces / updates a share of the bucket).  Needs the push inbox when world > 1.
-        self.fused_tail = os.environ.get("B200DIST_FUSED_TAIL", "1") != "0" and (self.world == 1 or self.inbox_handle is not None)
+        # deterministic=True: every step CTA stores its gradient sums to a private slot and `det_reduce` adds the slots in
+        # CTA order (instead of float red.add into one bucket) => two runs with the same seed are bit-identical, at the
+        # price of one more small kernel and 128 x 87 KB of extra traffic per step.  (step()/graph path; the C++ executor
+        # and the fused tail keep the atomic flush.)
+        self.deterministic = bool(deterministic)
+        self.det_partials = torch.zeros(148 * NPAR_ALLOC, dtype=torch.float32, device=self.device) if deterministic else None
+        # opt-in (B200DIST_FUSED_TAIL=1): measured on B200 the grid-wide check-in costs more than the PDL hand-off to the
+        # separate optimizer kernel it removes (29.9 vs 28.1 us/step at 1 GPU, profiles/fused_tail.json), and it needs every
+        # CTA resident, which 8-CTA clusters do not guarantee.
+        self.fused_tail = (os.environ.get("B200DIST_FUSED_TAIL", "0") == "1" and not deterministic and self.cluster <= 4
+                           and (self.world == 1 or self.inbox_handle is not None))
         self.ticket = torch.zeros(2, dtype=torch.int32, device=self.device)
         self.gpu_launches_per_step = 1 if self.fused_tail else 2     # convnet_step (+ allreduce_sgd)
         self._warm()
@@ -225,8 +236,14 @@ class FusedTrainer:
             self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
                                 self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux, tail)
             return
-        self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
-                            self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux)
+        if self.deterministic and B * cl <= 148:
+            self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
+                                self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux,
+                                None, self.det_partials)
+            self.C.det_reduce(self.det_partials, B * cl, self.grads, self.step_counter, self.grad_stride)
+        else:
+            self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
+                                self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
                              self.done_counter, self.aux, self._inbox_ptrs)
@@ -339,10 +356,12 @@ class FusedTrainer:
             if loader.batch_size != self.bsz:
                 raise ValueError("loader batch size != trainer batch size")
             block = (int(loader._l.block_bytes()) + 255) // 256 * 256
-            # chunk pipeline (csrc/executor.cpp): K steps = 3 graph launches (K H2D nodes | 2K kernels | K D2H nodes) on
-            # three streams.  K = a third of the loader ring (<= 8); B200DIST_EXEC_CHUNK overrides (1 = per-step launches).
+            # Default: per-step issue with plain PDL stream launches (csrc/executor.cpp "direct mode"): measured on B200 that is
+            # the fastest way to feed the GPU (profiles/e2e_executor.json: 31 us/step with a graph per step, ~28 us/step device
+            # time; K-step chunk graphs pay ~3-6 us of device time per graph node at every boundary and came out SLOWER:
+            # 34.7 us/step at K = 8).  B200DIST_EXEC_CHUNK=K (2..8) selects the chunk pipeline anyway.
             env = os.environ.get("B200DIST_EXEC_CHUNK")
-            chunk = int(env) if env is not None else loader.num_buffers // 3
+            chunk = int(env) if env is not None else 1
             chunk = max(1, min(8, chunk))
             while chunk > 1 and loader.num_buffers < 3 * chunk:
                 chunk -= 1
