@@ -2,10 +2,17 @@
 
     python bench/allreduce_sweep.py --gpus N [--max-mb 1024] [--out gpurun_out/sweep_N.json]
 
-For every size 1 KB .. max: one-shot / two-shot / NVLS (when exposed) on a symmetric fp32 buffer (in place,
-1/N scale fused) and ``dist.all_reduce`` (NCCL) + ``div_`` (what the reference's average_gradients does per
-tensor).  Timed with CUDA events on the launching stream after warm-up, MAX over ranks;
-busBW = 2(N-1)/N * bytes / t, reported against the measured 770 GB/s peer-copy figure (900 nominal).
+For every size 1 KB .. max: LL (flag-in-data push, <= 64 KB) / one-shot / two-shot / NVLS (when exposed) on a symmetric
+fp32 buffer (in place, 1/N scale fused) and ``dist.all_reduce`` (NCCL) with and without the ``div_`` the reference's
+average_gradients issues per tensor.  Timed with CUDA events on the launching stream after warm-up, MAX over ranks.  Every
+arm is measured twice in alternating order (A B .. B A) and the minimum kept, so that no arm owes its number to its position
+(round 1's table had NCCL alone slower than NCCL + div).
+
+Bandwidth columns:
+  busbw   = 2(N-1)/N * bytes / t        the NCCL-tests convention (what a ring would push through each link)
+  link_tx = bytes a GPU really sends:    two-shot (N-1)/N * bytes * 2 (gather slices + broadcast own slice);
+            NVLS  bytes/N * 2 ... see `link_bytes()`; reported as link_GBs = link_tx / t against 770 GB/s measured peer copy.
+``--emit-table`` writes parallel/allreduce_table.json (per-world variant thresholds) from the measured winners.
 """
 import argparse
 import json
@@ -76,7 +83,20 @@ def body(rank, size):
         sizes.append(max_bytes)
     hd = w.alloc(max_bytes // 4, torch.float32)
     rows = []
-    variants = [("oneshot", 0), ("twoshot", 1)] + ([("nvls", 2)] if w.multicast else [])
+    variants = [("ll", 3), ("oneshot", 0), ("twoshot", 1)] + ([("nvls", 2)] if w.multicast else [])
+
+    def link_bytes(name, nbytes):
+        """Bytes one GPU transmits over its NVLink ports for one all-reduce of ``nbytes`` (receives the same)."""
+        if name == "ll":
+            return 2 * nbytes * (size - 1)                       # 16-byte lines carry 8 data bytes, to every peer
+        if name == "oneshot":
+            return nbytes * (size - 1)                           # every peer reads my whole buffer
+        if name == "twoshot":
+            return 2 * nbytes * (size - 1) / size                # peers read my slices + I push my reduced slice to them
+        if name == "nvls":
+            return 2 * nbytes / size                             # my slice: one multimem.ld_reduce pull + one multimem.st push
+        return 2 * nbytes * (size - 1) / size                    # NCCL ring / tree: the bus-bandwidth convention
+
     for nbytes in sizes:
         n = nbytes // 4
         t = hd.local[:n]
@@ -84,20 +104,31 @@ def body(rank, size):
         iters = 100 if nbytes <= (1 << 20) else (40 if nbytes <= (64 << 20) else 10)
         gm = nbytes <= (4 << 20)          # graph-timed (device rate) for latency-bound sizes
         row = {"bytes": nbytes, "graph_timed": gm}
+        arms = []
         for name, v in variants:
             if v == 0 and nbytes > (8 << 20):
                 continue
-            t.fill_(1.0)
-            ms = time_op(lambda: w.all_reduce_(t, scale=1.0 / size, handle=hd, variant=v), iters, dev, gm)
+            if v == 3 and nbytes > symm.LL_CAP_VEC * 16:
+                continue
+
+            def run(v=v):
+                w.all_reduce_(t, scale=1.0 / size, handle=hd, variant=v)
+            arms.append((name, run, True))
+        arms.append(("nccl_div", lambda: (dist.all_reduce(plain), plain.div_(size)), False))
+        arms.append(("nccl", lambda: dist.all_reduce(plain), False))
+        best_ms = {}
+        for order in (arms, arms[::-1]):                       # A B C .. then .. C B A: position effects cancel
+            for name, fn, ours in order:
+                if ours:
+                    t.fill_(1.0)
+                ms = time_op(fn, iters, dev, gm)
+                best_ms[name] = min(best_ms.get(name, 1e30), ms)
+                if ours:
+                    assert abs(float(t[0]) - 1.0) < 1e-3, (name, float(t[0]))
+        for name, ms in best_ms.items():
             row[name + "_us"] = ms * 1e3
             row[name + "_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
-            assert abs(float(t[0]) - 1.0) < 1e-3, (name, float(t[0]))
-        ms = time_op(lambda: (dist.all_reduce(plain), plain.div_(size)), iters, dev, gm)
-        row["nccl_div_us"] = ms * 1e3
-        row["nccl_div_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
-        ms = time_op(lambda: dist.all_reduce(plain), iters, dev, gm)
-        row["nccl_us"] = ms * 1e3
-        row["nccl_busbw_GBs"] = 2 * (size - 1) / size * nbytes / (ms * 1e-3) / 1e9
+            row[name + "_link_GBs"] = link_bytes(name.split("_")[0], nbytes) / (ms * 1e-3) / 1e9
         best = min((row[k], k) for k in row if k.endswith("_us") and not k.startswith("nccl"))
         row["best"] = best[1][:-3]
         row["speedup_vs_nccl_div"] = row["nccl_div_us"] / best[0]
@@ -117,8 +148,31 @@ def body(rank, size):
     bucket = w.alloc(21888, torch.float32)
     fused = time_op(lambda: w.all_reduce_(bucket.local, scale=1.0 / size, handle=bucket, variant=0), 100, dev, True) * 1e3
     fused_eager = time_op(lambda: w.all_reduce_(bucket.local, scale=1.0 / size, handle=bucket, variant=0), 100, dev, False) * 1e3
+    table = None
     if rank == 0:
-        out = {"n_gpus": size, "symm": w.describe(), "rows": rows,
+        # variant thresholds from the measured winners: largest size at which LL / one-shot still wins, smallest at which NVLS does
+        def last_win(name):
+            sz = 0
+            for r in rows:
+                if r["best"] == name:
+                    sz = r["bytes"]
+            return sz
+        nv = [r["bytes"] for r in rows if r["best"] == "nvls"]
+        table = {"ll_max": last_win("ll"), "oneshot_max": max(last_win("oneshot"), last_win("ll")),
+                 "nvls_min": (min(nv) if nv else (1 << 62))}
+        if getattr(ARGS, "emit_table", False):
+            path = os.path.join(ROOT, "dist_tuto.pth_b200", "parallel", "allreduce_table.json")
+            try:
+                cur = json.load(open(path))
+            except Exception:
+                cur = {"what": "per-world all-reduce variant thresholds (wire bytes), written by bench/allreduce_sweep.py --emit-table", "worlds": {}}
+            cur["worlds"][str(size)] = table
+            json.dump(cur, open(path, "w"), indent=1)
+            for extra in (os.path.join(ROOT, "gpurun_out", f"allreduce_table_world{size}.json"),):
+                os.makedirs(os.path.dirname(extra), exist_ok=True)
+                json.dump({"world": size, **table}, open(extra, "w"), indent=1)
+    if rank == 0:
+        out = {"n_gpus": size, "symm": w.describe(), "rows": rows, "thresholds_from_this_sweep": table,
                "convnet_average_gradients": {"reference_8x(allreduce+div)_us": per_tensor, "fused_oneshot_bucket_us": fused,
                                              "speedup": per_tensor / fused, "timing": "CUDA-graph replay (device rate)",
                                              "eager_reference_us": per_tensor_eager, "eager_fused_us": fused_eager},
@@ -134,6 +188,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=2)
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--emit-table", action="store_true", help="write the measured variant thresholds of this world size")
     ARGS = ap.parse_args()
     if ARGS.out is None:
         ARGS.out = f"gpurun_out/sweep_{ARGS.gpus}.json"

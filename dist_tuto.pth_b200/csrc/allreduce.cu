@@ -10,10 +10,14 @@
 //   one-shot : every rank reads the whole buffer of every peer           (latency-optimal, <= ~256 KB)
 //   two-shot : reduce-scatter (rank r owns slice r) + push all-gather    (2(N-1)/N * M bytes per GPU)
 //   NVLS     : multimem.ld_reduce + multimem.st on a multicast address   (the switch does the sum)
+//   LL       : flag-in-data push for small messages -- every rank STORES its vectors into every peer's inbox as 16-byte
+//              lines {d0, epoch, d1, epoch} and reduces out of its own memory: no barrier, ONE NVLink crossing on the
+//              critical path (the barrier variants need a flag crossing plus a load round trip)
 //
 // Work mapping invariant: element-vector j of a slice is always handled by the same (block, thread) on
 // every rank and in every phase, which is what makes the *per-block* cross-GPU barriers sufficient.
 #include <cstdio>
+#include <cstring>
 #include "common.cuh"
 
 namespace b2 {
@@ -99,6 +103,8 @@ struct ARArgs {
   float scale;
   int rank, world;
   int src_f32, dst_f32;   // local dtypes: 1 = fp32, 0 = wire dtype
+  PeerPtrs inbox;         // LL variant: every rank's inbox [2 parities][world sources][ll_cap vectors][2 lines of 16 B]
+  size_t ll_cap;          // vectors per (parity, source) region of the inbox
 };
 
 constexpr int kThreads = 512;
@@ -236,6 +242,72 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(ARArgs a) {
   if (threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
 }
 
+// ------------------------------------------------------------------------------------------ LL (flag-in-data push)
+// Every vector is handled by the same (block, thread) on all ranks and each block keeps its own call counter (the signal
+// pad's per-block epoch word, shared with the barrier variants, which only ever compare epochs with >=), so sender and
+// receiver of a line agree on epoch and parity without any cross-block coordination.  Parity double-buffers the inbox: a
+// peer can write my parity-p region of block b again only two participations of block b later, which needs my lines of the
+// participation in between, which I store after I finished reading parity p (same argument as sgd_device.cuh, model-checked
+// in tests/test_protocol_models.py).  epoch 0 never occurs as a flag: counters are pre-incremented and the inbox starts zeroed.
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads) allreduce_ll_kernel(ARArgs a) {
+  using W = Wire<BF16>;
+  const int rank = a.rank, world = a.world;
+  const uint32_t epoch = barrier_epoch_load(a.sig, rank) + 1u;
+  const uint32_t flag = epoch == 0u ? 1u : epoch;                     // 0 is "never written"
+  const size_t par = (size_t)(epoch & 1u);
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const void* in_local = a.src != nullptr ? a.src : a.bufs.p[rank];
+  const bool in_f32 = a.src != nullptr && a.src_f32 != 0;
+  void* out = a.dst != nullptr ? a.dst : a.bufs.p[rank];
+  const bool out_f32 = a.dst != nullptr && a.dst_f32 != 0;
+  for (size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x; v < a.n_vec; v += stride) {
+    const uint4 mine = load_local_as_wire<BF16>(in_local, v, in_f32);
+    const uint4 l0 = make_uint4(mine.x, flag, mine.y, flag), l1 = make_uint4(mine.z, flag, mine.w, flag);
+    const size_t line = ((par * (size_t)world + (size_t)rank) * a.ll_cap + v) * 2;
+#pragma unroll
+    for (int i = 1; i < B2_MAX_RANKS; ++i) {
+      if (i < world) {
+        int r = rank + i;
+        if (r >= world) r -= world;
+        uint4* d = reinterpret_cast<uint4*>(a.inbox.p[r]) + line;
+        st_volatile_v4(d, l0);
+        st_volatile_v4(d + 1, l1);
+      }
+    }
+    float acc[W::kElems];
+    W::zero(acc);
+    const uint4* in = reinterpret_cast<const uint4*>(a.inbox.p[rank]);
+#pragma unroll
+    for (int r = 0; r < B2_MAX_RANKS; ++r) {
+      if (r < world) {
+        uint4 w;
+        if (r == rank) {
+          w = mine;
+        } else {
+          const uint4* src = in + ((par * (size_t)world + (size_t)r) * a.ll_cap + v) * 2;
+          uint4 q0, q1;
+          unsigned long long spins = 0;
+          for (;;) {
+            q0 = ld_volatile_v4(src);
+            q1 = ld_volatile_v4(src + 1);
+            if (q0.y == flag && q0.w == flag && q1.y == flag && q1.w == flag) break;
+            if (++spins > B2_SPIN_LIMIT) {
+              printf("[b200dist] LL all-reduce: rank %d timed out waiting for rank %d (block %d, epoch %u)\n", rank, r, (int)blockIdx.x, flag);
+              __trap();
+            }
+          }
+          w = make_uint4(q0.x, q0.z, q1.x, q1.z);
+        }
+        W::add(acc, w);                                               // fixed rank order => bit-identical on every rank
+      }
+    }
+    store_acc_local<BF16>(out, v, acc, a.scale, out_f32);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) barrier_epoch_store(a.sig, rank, epoch);
+}
+
 // ------------------------------------------------------------------------------------------ barrier only
 __global__ void __launch_bounds__(32) barrier_kernel(SignalPads sig, int rank, int world) {
   uint32_t epoch = barrier_epoch_load(sig, rank);
@@ -248,17 +320,24 @@ __global__ void __launch_bounds__(32) barrier_kernel(SignalPads sig, int rank, i
 // ============================================================================================ launchers
 extern "C" {
 
-// variant: 0 one-shot, 1 two-shot, 2 NVLS.  Returns cudaError_t as int.
+// variant: 0 one-shot, 1 two-shot, 2 NVLS, 3 LL (needs inbox / ll_cap).  Returns cudaError_t as int.
 int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const b2::SignalPads* sig, void* mc,
                         const void* src, int src_f32, void* dst, int dst_f32, size_t n_vec, float scale,
-                        int rank, int world, int max_blocks, cudaStream_t stream) {
+                        int rank, int world, int max_blocks, const PeerPtrs* inbox, size_t ll_cap, cudaStream_t stream) {
   b2::ARArgs a;
+  memset(&a.inbox, 0, sizeof(a.inbox));
+  a.ll_cap = 0;
   a.bufs = *bufs; a.sig = *sig; a.mc = mc; a.src = src; a.dst = dst; a.n_vec = n_vec; a.scale = scale;
   a.rank = rank; a.world = world; a.src_f32 = src_f32; a.dst_f32 = dst_f32;
+  if (variant == 3) {
+    if (inbox == nullptr || ll_cap < n_vec) return (int)cudaErrorInvalidValue;
+    a.inbox = *inbox;
+    a.ll_cap = ll_cap;
+  }
   if (max_blocks <= 0 || max_blocks > B2_MAX_BLOCKS) max_blocks = B2_MAX_BLOCKS;
-  const size_t work = (variant == 0) ? n_vec : n_vec / world;
+  const size_t work = (variant == 0 || variant == 3) ? n_vec : n_vec / world;
   size_t blocks = (work + b2::kThreads - 1) / b2::kThreads;
-  if (variant != 0) blocks = (blocks + 1) / 2;
+  if (variant == 1 || variant == 2) blocks = (blocks + 1) / 2;
   if (blocks < 1) blocks = 1;
   if (blocks > (size_t)max_blocks) blocks = max_blocks;
   dim3 grid((unsigned)blocks), block(b2::kThreads);
@@ -268,6 +347,9 @@ int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const b2::S
   } else if (variant == 1) {
     if (bf16) b2::allreduce_twoshot_kernel<true, false><<<grid, block, 0, stream>>>(a);
     else b2::allreduce_twoshot_kernel<false, false><<<grid, block, 0, stream>>>(a);
+  } else if (variant == 3) {
+    if (bf16) b2::allreduce_ll_kernel<true><<<grid, block, 0, stream>>>(a);
+    else b2::allreduce_ll_kernel<false><<<grid, block, 0, stream>>>(a);
   } else {
     if (mc == nullptr) return (int)cudaErrorInvalidValue;
     if (bf16) b2::allreduce_twoshot_kernel<true, true><<<grid, block, 0, stream>>>(a);

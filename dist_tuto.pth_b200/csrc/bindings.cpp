@@ -38,7 +38,7 @@ int b2_ipc_free(unsigned long long ptr);
 
 int b2_allreduce_launch(int variant, int bf16, const PeerPtrs* bufs, const SignalPadsH* sig, void* mc, const void* src,
                         int src_f32, void* dst, int dst_f32, size_t n_vec, float scale, int rank, int world,
-                        int max_blocks, cudaStream_t stream);
+                        int max_blocks, const PeerPtrs* inbox, size_t ll_cap, cudaStream_t stream);
 int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t stream);
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
@@ -54,7 +54,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
                            const void* tail, float* det_partials, cudaStream_t stream);
 int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stride, float* grads, const unsigned long long* step,
-                         long long grad_stride, size_t n_elems, cudaStream_t stream);
+                         long long grad_stride, size_t n_elems, float* loss_acc, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
@@ -268,15 +268,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // ------------------------------------------------------------------ collectives
   m.def("allreduce", [](int variant, bool bf16, std::vector<unsigned long long> bufs, std::vector<unsigned long long> sigs,
                         unsigned long long mc, c10::optional<torch::Tensor> src, c10::optional<torch::Tensor> dst,
-                        size_t n_vec, double scale, int rank, int world, int max_blocks) {
+                        size_t n_vec, double scale, int rank, int world, int max_blocks, std::vector<unsigned long long> inbox,
+                        size_t ll_cap) {
     PeerPtrs b = to_ptrs(bufs); SignalPadsH s = to_sig(sigs);
+    PeerPtrs ib = to_ptrs(inbox);
     const void* sp = nullptr; void* dp = nullptr; int sf = 0, df = 0;
     if (src.has_value()) { check_cuda_contig(*src, "src"); sp = src->data_ptr(); sf = src->scalar_type() == torch::kFloat32 && bf16; }
     if (dst.has_value()) { check_cuda_contig(*dst, "dst"); dp = dst->data_ptr(); df = dst->scalar_type() == torch::kFloat32 && bf16; }
     ck_cuda(b2_allreduce_launch(variant, bf16, &b, &s, (void*)(uintptr_t)mc, sp, sf, dp, df, n_vec, (float)scale, rank,
-                                world, max_blocks, cur_stream()), "allreduce launch");
+                                world, max_blocks, inbox.empty() ? nullptr : &ib, ll_cap, cur_stream()), "allreduce launch");
   }, py::arg("variant"), py::arg("bf16"), py::arg("bufs"), py::arg("sigs"), py::arg("mc"), py::arg("src"), py::arg("dst"),
-     py::arg("n_vec"), py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("max_blocks") = 0);
+     py::arg("n_vec"), py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("max_blocks") = 0,
+     py::arg("inbox") = std::vector<unsigned long long>(), py::arg("ll_cap") = 0);
   m.def("barrier", [](std::vector<unsigned long long> sigs, int rank, int world) {
     SignalPadsH s = to_sig(sigs);
     ck_cuda(b2_barrier_launch(&s, rank, world, cur_stream()), "barrier launch");
@@ -390,15 +393,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
      py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none(),
      py::arg("tail") = py::none(), py::arg("det_partials") = py::none());
-  m.def("det_reduce", [](torch::Tensor partials, int n_slots, torch::Tensor grads, c10::optional<torch::Tensor> step, int64_t grad_stride) {
+  m.def("det_reduce", [](torch::Tensor partials, int n_slots, torch::Tensor grads, c10::optional<torch::Tensor> step, int64_t grad_stride,
+                         c10::optional<torch::Tensor> loss_acc) {
     // deterministic mode: grads[(step & 1) * grad_stride ...] = sum over the first n_slots per-CTA slots, in slot order
     check_cuda_contig(partials, "partials"); check_cuda_contig(grads, "grads");
     TORCH_CHECK(partials.scalar_type() == torch::kFloat32 && grads.scalar_type() == torch::kFloat32 && partials.numel() >= (int64_t)n_slots * 21888);
     const unsigned long long* st = step.has_value() ? reinterpret_cast<const unsigned long long*>(step->data_ptr()) : nullptr;
     c10::cuda::CUDAGuard guard(grads.device());
+    float* la = loss_acc.has_value() ? loss_acc->data_ptr<float>() : nullptr;
     ck_cuda(b2_det_reduce_launch(partials.data_ptr<float>(), n_slots, 21888, grads.data_ptr<float>(), st, grad_stride,
-                                 (size_t)b2_convnet_npar(), cur_stream()), "det_reduce launch");
-  }, py::arg("partials"), py::arg("n_slots"), py::arg("grads"), py::arg("step") = py::none(), py::arg("grad_stride") = 0);
+                                 (size_t)b2_convnet_npar(), la, cur_stream()), "det_reduce launch");
+  }, py::arg("partials"), py::arg("n_slots"), py::arg("grads"), py::arg("step") = py::none(), py::arg("grad_stride") = 0,
+     py::arg("loss_acc") = py::none());
 
   // ------------------------------------------------------------------ tcgen05 GEMM
   m.def("gemm_available", [] { return b2_gemm_available() != 0; });

@@ -719,8 +719,13 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     }
   }
   if (tid == 0 && a.loss_acc != nullptr && blockIdx.x < a.B) {
-    atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
-    atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+    if (a.det_partials != nullptr && a.backward) {       // deterministic mode: the slot's padding carries this CTA's loss terms
+      a.det_partials[(size_t)blockIdx.x * DET_STRIDE + NPAR] = s.loss_local * a.inv_bsz;
+      a.det_partials[(size_t)blockIdx.x * DET_STRIDE + NPAR + 1] = (float)s.correct_local;
+    } else {
+      atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
+      atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+    }
   }
   // ------------------------------------------------------------------ fused tail: gradient exchange + SGD in this kernel
   if (a.tail.enabled && a.backward) b2::fused_tail(a.tail, step, (int)gridDim.x, (int)blockIdx.x);   // grid <= B: every CTA flushed

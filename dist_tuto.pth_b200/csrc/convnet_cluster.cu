@@ -521,9 +521,14 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     flush(W4 + cr * K::W4_PER, W4 + min(500, (cr + 1) * K::W4_PER));
     if (cr == 0) { flush(B2, B2 + 20); flush(B4, B4 + 10); }
   }
-  if (tid == 0 && cr == 0 && a.loss_acc != nullptr && cluster_id < a.B) {
-    atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
-    atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+  if (tid == 0 && a.loss_acc != nullptr && cluster_id < a.B) {
+    if (a.det_partials != nullptr && a.backward) {       // deterministic mode: the slot's padding carries the loss terms
+      a.det_partials[(size_t)blockIdx.x * DET_STRIDE + NPAR] = cr == 0 ? s.loss_local * a.inv_bsz : 0.f;
+      a.det_partials[(size_t)blockIdx.x * DET_STRIDE + NPAR + 1] = cr == 0 ? (float)s.correct_local : 0.f;
+    } else if (cr == 0) {
+      atomicAdd(a.loss_acc, s.loss_local * a.inv_bsz);
+      atomicAdd(a.loss_acc + 1, (float)s.correct_local);
+    }
   }
   cl.sync();                                       // no CTA exits while a peer may still address its shared memory
   // fused tail: gradient exchange + SGD in this kernel (every cluster carried >= 1 sample: gridDim.x / C <= B)

@@ -110,10 +110,19 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs
 // order of the exchange the whole update -- is bit-reproducible from run to run (float red.add into one bucket is not).
 __global__ void __launch_bounds__(256) det_reduce_kernel(const float* __restrict__ partials, int n_slots, long long slot_stride,
                                                          float* __restrict__ grads, const unsigned long long* __restrict__ step,
-                                                         long long grad_stride, int n_vec) {
+                                                         long long grad_stride, int n_vec, float* __restrict__ loss_acc) {
   pdl_wait();
   pdl_launch_dependents();
   const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v == n_vec && loss_acc != nullptr) {        // the vector behind the parameters: {batch-mean nll, #correct} of every CTA
+    float l = 0.f, c = 0.f;
+    for (int sl = 0; sl < n_slots; ++sl) {
+      l += __ldcg(partials + (size_t)sl * slot_stride + (size_t)n_vec * 4);
+      c += __ldcg(partials + (size_t)sl * slot_stride + (size_t)n_vec * 4 + 1);
+    }
+    loss_acc[0] += l;                             // the only writer of loss_acc while this kernel runs
+    loss_acc[1] += c;
+  }
   if (v >= n_vec) return;
   const unsigned long long st = step != nullptr ? *step : 0ull;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -191,11 +200,11 @@ int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, fl
 }
 
 int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stride, float* grads, const unsigned long long* step,
-                         long long grad_stride, size_t n_elems, cudaStream_t stream) {
+                         long long grad_stride, size_t n_elems, float* loss_acc, cudaStream_t stream) {
   const int n_vec = (int)(n_elems / 4);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)((n_vec + 255) / 256));
+  cfg.gridDim = dim3((unsigned)((n_vec + 1 + 255) / 256));
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -203,7 +212,7 @@ int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stri
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, b2::det_reduce_kernel, partials, n_slots, slot_stride, grads, step, grad_stride, n_vec);
+  return (int)cudaLaunchKernelEx(&cfg, b2::det_reduce_kernel, partials, n_slots, slot_stride, grads, step, grad_stride, n_vec, loss_acc);
 }
 
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,

@@ -240,7 +240,7 @@ class FusedTrainer:
             self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
                                 self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux,
                                 None, self.det_partials)
-            self.C.det_reduce(self.det_partials, B * cl, self.grads, self.step_counter, self.grad_stride)
+            self.C.det_reduce(self.det_partials, B * cl, self.grads, self.step_counter, self.grad_stride, self.loss_acc)
         else:
             self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
                                 self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux)

@@ -35,7 +35,19 @@ from ..ops import _ext
 __all__ = ["SymmWorld", "SymmHandle", "init_world", "lookup_world", "destroy_all", "VARIANTS"]
 
 PAD_BYTES = 8192                      # signal pad at the head of every allocation (B2_SIGNAL_WORDS*4 = 6016 B)
-VARIANTS = {"oneshot": 0, "twoshot": 1, "nvls": 2}
+VARIANTS = {"oneshot": 0, "twoshot": 1, "nvls": 2, "ll": 3}
+LL_CAP_VEC = 4096                     # LL (flag-in-data) inbox capacity per (parity, source): 4096 x 16 B = 64 KB messages
+_TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "allreduce_table.json")
+
+
+def _load_table():
+    """Per-world variant thresholds measured by bench/allreduce_sweep.py --emit-table (wire bytes)."""
+    try:
+        import json
+        with open(_TABLE_PATH) as f:
+            return {int(k): v for k, v in json.load(f).get("worlds", {}).items()}
+    except Exception:
+        return {}
 _WORLDS: Dict[object, "SymmWorld"] = {}
 _DTYPES = (torch.float32, torch.bfloat16)
 
@@ -52,6 +64,7 @@ class SymmHandle:
 
     def __init__(self, world, nbytes, size, ptrs, mc_ptr, mem_handles, mc_handle, mode):
         self.world, self.nbytes, self.size = world, nbytes, size
+        self.ll: Optional["SymmHandle"] = None               # inbox of the LL (flag-in-data) variant, if any
         self.base_ptrs: List[int] = ptrs                     # allocation bases (signal pads) per rank
         self.ptrs: List[int] = [p + PAD_BYTES for p in ptrs]  # data bases per rank
         self.sig_ptrs: List[int] = ptrs
@@ -124,8 +137,19 @@ class SymmWorld:
         # size thresholds (wire bytes) from the measured sweeps (profiles/n2, profiles/n8; bench/allreduce_sweep.py):
         #   2 GPUs : one-shot wins up to ~64 KB, two-shot above; NVLS never beats two-shot (no fan-in to amortise)
         #   8 GPUs : one-shot wins up to ~8 KB; above that NVLS (in-switch reduction) wins at every size, two-shot next
-        self.oneshot_max = _env_int("B200DIST_ONESHOT_MAX", (64 << 10) if self.world <= 2 else (8 << 10))
-        self.nvls_min = _env_int("B200DIST_NVLS_MIN", (1 << 62) if self.world <= 2 else (8 << 10) + 1)
+        # ... superseded per world size by the table bench/allreduce_sweep.py --emit-table writes (nearest measured world)
+        defaults = {"ll_max": 32 << 10, "oneshot_max": (64 << 10) if self.world <= 2 else (8 << 10),
+                    "nvls_min": (1 << 62) if self.world <= 2 else (8 << 10) + 1}
+        table = _load_table()
+        if table:
+            near = min(table, key=lambda k: (abs(k - self.world), -k))
+            defaults.update({k: int(v) for k, v in table[near].items() if k in defaults})
+            self.table_world = near
+        else:
+            self.table_world = None
+        self.ll_max = min(_env_int("B200DIST_LL_MAX", defaults["ll_max"]), LL_CAP_VEC * 16)
+        self.oneshot_max = _env_int("B200DIST_ONESHOT_MAX", defaults["oneshot_max"])
+        self.nvls_min = _env_int("B200DIST_NVLS_MIN", defaults["nvls_min"])
         self.nvls_error: Optional[str] = None
 
     # ------------------------------------------------------------------ plumbing
@@ -157,8 +181,10 @@ class SymmWorld:
         return got
 
     # ------------------------------------------------------------------ allocation
-    def alloc_bytes(self, nbytes: int) -> SymmHandle:
-        """Collective: allocate ``nbytes`` of symmetric data (+ a private signal pad)."""
+    def alloc_bytes(self, nbytes: int, ll: bool = True) -> SymmHandle:
+        """Collective: allocate ``nbytes`` of symmetric data (+ a private signal pad; + with ``ll`` the 2 MB inbox of the
+        small-message flag-in-data variant, allocated here rather than lazily so that no collective set-up can land inside a
+        CUDA-graph capture)."""
         C, dev = self.C, self.device.index
         nbytes = (int(nbytes) + 255) // 256 * 256 + 256       # slack for world-multiple vector padding
         size = (PAD_BYTES + nbytes + self.gran - 1) // self.gran * self.gran
@@ -201,6 +227,8 @@ class SymmWorld:
         if self.world > 1:
             dist.barrier(group=self.group)
         self._handles.append(hd)
+        if ll and self.world > 1:
+            hd.ll = self.alloc_bytes(2 * self.world * LL_CAP_VEC * 32, ll=False)
         return hd
 
     def _agree(self, ok: bool) -> bool:
@@ -301,6 +329,8 @@ class SymmWorld:
         if forced in VARIANTS:
             v = VARIANTS[forced]
             return v if (v != 2 or self.multicast) else 1
+        if wire_bytes <= self.ll_max:
+            return 3
         if wire_bytes <= self.oneshot_max:
             return 0
         return 2 if (self.multicast and wire_bytes >= self.nvls_min) else 1
@@ -311,10 +341,16 @@ class SymmWorld:
         v = self.pick_variant(wire_bytes) if variant is None else variant
         if v == 2 and not hd.mc_ptr:
             v = 1
-        if v != 0:
+        if v == 3 and (hd.ll is None or n_vec > LL_CAP_VEC):
+            v = 0
+        if v in (1, 2):
             n_vec = (n_vec + self.world - 1) // self.world * self.world
-        self.C.allreduce(v, bf16, hd.ptrs, hd.sig_ptrs, hd.mc_ptr, src, dst, n_vec, float(scale), self.rank,
-                         self.world, self.max_blocks if max_blocks is None else max_blocks)
+        if v == 3:
+            self.C.allreduce(v, bf16, hd.ptrs, hd.sig_ptrs, hd.mc_ptr, src, dst, n_vec, float(scale), self.rank,
+                             self.world, self.max_blocks if max_blocks is None else max_blocks, hd.ll.ptrs, LL_CAP_VEC)
+        else:
+            self.C.allreduce(v, bf16, hd.ptrs, hd.sig_ptrs, hd.mc_ptr, src, dst, n_vec, float(scale), self.rank,
+                             self.world, self.max_blocks if max_blocks is None else max_blocks)
         return v
 
     def all_reduce_(self, t: torch.Tensor, scale: float = 1.0, handle: Optional[SymmHandle] = None,
@@ -372,7 +408,8 @@ class SymmWorld:
     def describe(self) -> dict:
         """What was negotiated at setup (mapping mode, multicast, thresholds) -- recorded in bench / sweep outputs."""
         return {"world": self.world, "rank": self.rank, "mode": self.mode, "multicast": self.multicast,
-                "granularity": self.gran, "nvls_error": self.nvls_error, "oneshot_max": self.oneshot_max}
+                "granularity": self.gran, "nvls_error": self.nvls_error, "ll_max": self.ll_max,
+                "oneshot_max": self.oneshot_max, "nvls_min": self.nvls_min, "table_world": self.table_world}
 
     def destroy(self):
         """Unmap and release every symmetric allocation of this world (idempotent; called by ``launch.shutdown``)."""

@@ -21,7 +21,7 @@ def w_symm_allreduce(rank, size):
     info = w.describe()
     if rank == 0:
         print("SYMM", info, flush=True)
-    variants = [0, 1] + ([2] if w.multicast else [])
+    variants = [0, 1, 3] + ([2] if w.multicast else [])       # one-shot, two-shot, LL (falls back to one-shot > 64 KB), NVLS
     for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
         for n in (1, 7, 64, 1000, 21888, 65536 + 3, 1 << 20):
             g = torch.Generator(device="cpu").manual_seed(1000 + rank)
@@ -286,7 +286,7 @@ def w_suite_odd_world(rank, size):
     dev = _dev()
     w = symm.lookup_world(None)
     assert w is not None and w.world == size
-    variants = [0, 1] + ([2] if w.multicast else [])
+    variants = [0, 1, 3] + ([2] if w.multicast else [])       # one-shot, two-shot, LL (falls back to one-shot > 64 KB), NVLS
     for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
         for n in (1, 5, 64, 21888, 65536 + 3, (1 << 20) + 7):
             g = torch.Generator(device="cpu").manual_seed(1000 + rank)
@@ -321,7 +321,7 @@ def w_flag_reuse_stress(rank, size):
     then 20000 one-kernel training steps replayed from CUDA graphs (inbox epochs / parity double-buffer of the push exchange)."""
     dev = _dev()
     w = symm.lookup_world(None)
-    variants = [0, 1] + ([2] if w.multicast else [])
+    variants = [0, 1, 3] + ([2] if w.multicast else [])       # one-shot, two-shot, LL (falls back to one-shot > 64 KB), NVLS
     hd = w.alloc(4096, torch.float32)
     n_it = int(os.environ.get("B200DIST_STRESS_ITERS", "100000"))
     hd.local.fill_(1.0)

@@ -456,5 +456,5 @@ def test_deterministic_mode_is_bit_reproducible(dev, bsz):
         return tr.params.clone(), tr.momentum.clone(), tr.pop_loss_sum()
 
     a, b, c = run(True), run(True), run(False)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]      # parameters, momentum AND the loss sum
     assert torch.allclose(a[0], c[0], atol=2e-5, rtol=1e-4)

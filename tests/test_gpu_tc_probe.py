@@ -37,22 +37,57 @@ def _umma(a_img, b_img, idesc, ops, ncols):
     return out.cpu().numpy()
 
 
-def test_tma_4d_box_with_16_byte_inner_extent_is_address_swizzled():
-    """conv2's implicit im2col: box {8 x, 8 y, 16 c, 2 b} of the NCHW-padded activation [B,16,12,16] at (kx, ky, 0, b0)."""
+def _tma(t, dims, strides, box, swz, coords):
     C = _ext.C()
-    dev = torch.device("cuda", 0)
-    B = 4
-    t = np.arange(B * 16 * 12 * 16, dtype=np.uint16).reshape(B, 16, 12, 16)
-    tens = torch.from_numpy(t.view(np.int16)).to(dev)
-    kx, ky, b0 = 3, 2, 1
-    img = C.tma_probe(tens, [16, 12, 16, B], [32, 12 * 32, 16 * 12 * 32], [8, 8, 16, 2], 3, [kx, ky, 0, b0])
+    img = C.tma_probe(torch.from_numpy(t.view(np.int16)).to("cuda:0"), dims, strides, box, swz, coords)
     torch.cuda.synchronize()
-    got = img.cpu().numpy()
-    box = t[b0:b0 + 2, :, ky:ky + 8, kx:kx + 8]                    # [b, c, y, x]
-    want = L.expected_tma_image(box)
-    ok = bool(np.array_equal(got, want))
-    _report("tma_4d_sw128", {"ok": ok, "first_bytes_got": got[:64].tolist(), "first_bytes_want": want[:64].tolist()})
-    assert ok
+    return img.cpu().numpy()
+
+
+def test_tma_channel_last_boxes_are_address_swizzled():
+    """The boxes the batched engine issues (NHWC activations, 32-byte pixels, SWIZZLE_32B): a shifted 8x8 window of two
+    samples, the [y][b][x][c] image of the conv2-forward window descriptors, and zero fill past the batch.  (An x-innermost
+    box shifted by an odd number of elements FAULTS -- TMA needs a 16-byte aligned innermost start; profiles/probes.)"""
+    B = 5
+    t = (np.arange(B * 12 * 12 * 16, dtype=np.uint16) + 1).reshape(B, 12, 12, 16)
+    got = _tma(t, [16, 12, 12, B], [32, 384, 4608], [16, 8, 8, 2], 1, [0, 3, 2, 1])
+    assert np.array_equal(got, L.expected_tma_image_sw32(t[1:3, 2:10, 3:11, :]))
+    got = _tma(t, [16, 12, B, 12], [32, 4608, 384], [16, 12, 2, 12], 1, [0, 0, 2, 0])
+    assert np.array_equal(got, L.expected_tma_image_sw32(np.ascontiguousarray(t[2:4].transpose(1, 0, 2, 3))))
+    got = _tma(t, [16, 12, 12, B], [32, 384, 4608], [16, 8, 8, 2], 1, [0, 1, 1, 4])
+    box = np.zeros((2, 8, 8, 16), dtype=np.uint16)
+    box[0] = t[4, 1:9, 1:9, :]
+    assert np.array_equal(got, L.expected_tma_image_sw32(box))
+
+
+def test_umma_shifted_window_descriptors():
+    """conv2 forward: 25 taps = 25 K-major SWIZZLE_32B descriptors over ONE [y][b][x][c] image (start + ky*768 + kx*32,
+    SBO = 384); conv2 weight gradient: MN-major with 8 overlapping 16-channel atoms 32 bytes apart."""
+    rng = np.random.default_rng(6)
+    pix = _rand_bits(rng, (12, 2, 12, 16))
+    b = _rand_bits(rng, (32, 64))
+    ky, kx = 2, 3
+    d = _umma(L.expected_tma_image_sw32(pix), L.image_rows128(b), L.idesc_bf16(128, 32),
+              [(L.smem_desc(ky * 768 + kx * 32, 16, 384, 6), L.smem_desc(0, 16, 1024, 2), 0, 0)], 32)
+    pf, bf = L.bits_to_f32(pix), L.bits_to_f32(b)[:, :16]
+    ref = np.zeros((128, 32), np.float32)
+    for oy in range(8):
+        for bb in range(2):
+            for ox in range(8):
+                ref[(oy * 2 + bb) * 8 + ox] = pf[oy + ky, bb, ox + kx] @ bf.T
+    assert float(np.abs(d - ref).max() / np.abs(ref).max()) < 1e-3
+    pix1 = _rand_bits(rng, (12, 12, 16))
+    a_img = np.concatenate([L.expected_tma_image_sw32(pix1), np.zeros(1024, np.uint8)])
+    ky = 1
+    ops = [(L.smem_desc(ky * 384 + ks * 768, 32, 384, 6), L.smem_desc(ks * 32, 16, 1024, 2), 0, int(ks > 0)) for ks in range(4)]
+    d = _umma(a_img, L.image_rows128(b), L.idesc_bf16(128, 32, a_mn=1), ops, 32)
+    pf1, bfull = L.bits_to_f32(pix1).reshape(144, 16), L.bits_to_f32(b)
+    ref = np.zeros((80, 32), np.float32)
+    for kx in range(5):
+        for ci in range(16):
+            row = np.array([pf1[(oy + ky) * 12 + ox + kx, ci] for oy in range(8) for ox in range(8)], np.float32)
+            ref[kx * 16 + ci] = bfull @ row
+    assert float(np.abs(d[:80] - ref).max() / np.abs(ref).max()) < 1e-3
 
 
 def test_umma_kmajor_sw128_reference_mode():
