@@ -225,7 +225,7 @@ def ours(args):
                               e2e_value=e2e, h2d=h2d, d2h=8, gpu_launches=tr.gpu_launches_per_step * K, dtype="fp32",
                               extra_config={"engine": ("ONE kernel per step: fused convnet_step (cluster-per-sample for small per-GPU batches) whose tail does the gradient exchange + SGD; CUDA graph, PDL"
                                                        if tr.fused_tail else "fused convnet_step (cluster-per-sample for small per-GPU batches) + allreduce_sgd kernels, CUDA graph, PDL"),
-                                            "precision": "fp32 SIMT forward/backward (>= the required bf16); fp32 gradients on the wire; fp32 SGD",
+                                            "precision": "fp32 SIMT forward/backward (>= the required bf16); " + ("bf16" if tr.wire_bf16 else "fp32") + " gradients on the wire; fp32 accumulate + SGD",
                                             "cluster_ctas_per_sample": tr.cluster,
                                             "gradient_exchange": ("push: flag-in-data stores into peer inboxes, local reduce" if tr.inbox_handle is not None
                                                                   else ("barrier + peer loads" if size > 1 else "none (1 GPU)")),

@@ -132,6 +132,10 @@ def body(rank, size):
         best = min((row[k], k) for k in row if k.endswith("_us") and not k.startswith("nccl"))
         row["best"] = best[1][:-3]
         row["speedup_vs_nccl_div"] = row["nccl_div_us"] / best[0]
+        # graph-replayed back-to-back NCCL all-reduces of one buffer are reproducibly SLOWER than the same calls with the
+        # divide in between (both arm orders agree), so the competitor is the faster of the two NCCL arms
+        row["nccl_best_us"] = min(row["nccl_us"], row["nccl_div_us"])
+        row["speedup_vs_nccl_best"] = row["nccl_best_us"] / best[0]
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)

@@ -43,7 +43,7 @@ int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, cudaStream_t stream);
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -79,6 +79,7 @@ struct FusedTailHost {            // mirrors cn::FusedTailHost (csrc/convnet_arg
   unsigned int* ticket;
   float lr, mu, scale;
   int rank, world;
+  int wire_bf16;
 };
 struct BtBuffers {
   void *P1, *P2, *H, *DH, *dP2, *DC, *W2K, *W2R, *W3K, *W3T;
@@ -178,7 +179,7 @@ struct ExecutorPy {
              torch::Tensor done_counter, torch::Tensor loss_acc, torch::Tensor in_dev, bool raw_u8, bool training, int rank,
              int world, uint64_t seed, int64_t sample_base, int64_t grad_stride, double lr, double mu, double p_drop,
              int max_in_flight, int cluster, torch::Tensor aux, int chunk, std::vector<unsigned long long> inbox,
-             torch::Tensor loss_hist, bool fused_tail, torch::Tensor ticket)
+             torch::Tensor loss_hist, bool fused_tail, torch::Tensor ticket, bool wire_bf16)
       : loader(&l), keep{params, momentum, grads, step, done_counter, loss_acc, in_dev, aux, loss_hist, ticket} {
     TORCH_CHECK(l.impl->pinned(), "the native executor needs a pinned loader");
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
@@ -209,6 +210,7 @@ struct ExecutorPy {
     for (size_t i = 0; i < inbox.size() && i < 8; ++i) c.inbox_ptrs[i] = (void*)(uintptr_t)inbox[i];
     c.push = !inbox.empty();
     c.fused_tail = fused_tail ? 1 : 0;
+    c.wire_bf16 = wire_bf16 ? 1 : 0;
     if (fused_tail) {
       TORCH_CHECK(ticket.is_cuda() && ticket.scalar_type() == torch::kInt32 && ticket.numel() >= 2, "ticket: CUDA int32 [2]");
       TORCH_CHECK(world == 1 || c.push, "the fused tail needs the push inbox when world > 1");
@@ -287,7 +289,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_sgd", [](std::vector<unsigned long long> grads, std::vector<unsigned long long> sigs, torch::Tensor params,
                             torch::Tensor momentum, c10::optional<torch::Tensor> step, double lr, double mu, double scale,
                             int rank, int world, bool zero_grads, int64_t grad_stride, c10::optional<torch::Tensor> done_counter,
-                            c10::optional<torch::Tensor> aux, std::vector<unsigned long long> inbox) {
+                            c10::optional<torch::Tensor> aux, std::vector<unsigned long long> inbox, bool wire_bf16) {
     check_cuda_contig(params, "params"); check_cuda_contig(momentum, "momentum");
     TORCH_CHECK(inbox.empty() || (int)inbox.size() == world, "inbox: one pointer per rank (or none)");
     PeerPtrs ib = to_ptrs(inbox);
@@ -302,11 +304,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
                                     (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax,
-                                    inbox.empty() ? nullptr : &ib, nullptr, nullptr, cur_stream()),
+                                    inbox.empty() ? nullptr : &ib, nullptr, nullptr, wire_bf16 ? 1 : 0, cur_stream()),
             "allreduce_sgd launch");
   }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
      py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
-     py::arg("done_counter") = py::none(), py::arg("aux") = py::none(), py::arg("inbox") = std::vector<unsigned long long>());
+     py::arg("done_counter") = py::none(), py::arg("aux") = py::none(), py::arg("inbox") = std::vector<unsigned long long>(),
+     py::arg("wire_bf16") = false);
   m.def("sgd_flat", [](torch::Tensor p, torch::Tensor mom, torch::Tensor g, double lr, double mu, double wd, bool zero_grad) {
     check_cuda_contig(p, "p"); check_cuda_contig(mom, "m"); check_cuda_contig(g, "g");
     TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 && mom.scalar_type() == torch::kFloat32);
@@ -350,7 +353,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     const void* tp = nullptr;
     if (!tail.is_none()) {
       auto t = tail.cast<py::tuple>();
-      TORCH_CHECK(t.size() == 10, "tail: 10-tuple");
+      TORCH_CHECK(t.size() == 10 || t.size() == 11, "tail: 10/11-tuple");
+      th.wire_bf16 = 0;
       TORCH_CHECK(g != nullptr && st != nullptr && la != nullptr, "the fused tail needs grads, a step counter and loss_acc");
       auto gp = t[0].cast<std::vector<unsigned long long>>();
       auto ib = t[1].cast<std::vector<unsigned long long>>();
@@ -370,6 +374,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       th.loss_snapshot = t[9].is_none() ? nullptr : t[9].cast<torch::Tensor>().data_ptr<float>();
       th.ticket = reinterpret_cast<unsigned int*>(tick.data_ptr());
       th.lr = t[3].cast<float>(); th.mu = t[4].cast<float>(); th.scale = t[5].cast<float>();
+      th.wire_bf16 = t.size() > 10 ? (t[10].cast<bool>() ? 1 : 0) : 0;
       tp = &th;
     }
     float* dp = nullptr;
@@ -520,14 +525,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<LoaderPy&, torch::Tensor, torch::Tensor, torch::Tensor, std::vector<unsigned long long>,
                     std::vector<unsigned long long>, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, bool, bool,
                     int, int, uint64_t, int64_t, int64_t, double, double, double, int, int, torch::Tensor, int,
-                    std::vector<unsigned long long>, torch::Tensor, bool, torch::Tensor>(),
+                    std::vector<unsigned long long>, torch::Tensor, bool, torch::Tensor, bool>(),
            py::arg("loader"), py::arg("params"), py::arg("momentum"), py::arg("grads"), py::arg("grad_ptrs"),
            py::arg("sig_ptrs"), py::arg("step"), py::arg("done_counter"), py::arg("loss_acc"), py::arg("in_dev"),
            py::arg("raw_u8"), py::arg("training"), py::arg("rank"), py::arg("world"), py::arg("seed"),
            py::arg("sample_base"), py::arg("grad_stride"), py::arg("lr"), py::arg("mu"), py::arg("p_drop"),
            py::arg("max_in_flight") = 3, py::arg("cluster") = 1, py::arg("aux") = torch::Tensor(), py::arg("chunk") = 1,
            py::arg("inbox") = std::vector<unsigned long long>(), py::arg("loss_hist") = torch::Tensor(), py::arg("fused_tail") = false,
-           py::arg("ticket") = torch::Tensor(), py::keep_alive<1, 2>())
+           py::arg("ticket") = torch::Tensor(), py::arg("wire_bf16") = false, py::keep_alive<1, 2>())
       .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
       .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
       .def("stats", [](ExecutorPy& e) {

@@ -40,7 +40,7 @@ struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrsC* inbox, const float* loss_acc, float* loss_snapshot, cudaStream_t stream);
+                            const PeerPtrsC* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
@@ -59,6 +59,7 @@ struct FusedTailHostC {            // mirrors cn::FusedTailHost (csrc/convnet_ar
   unsigned int* ticket;
   float lr, mu, scale;
   int rank, world;
+  int wire_bf16;
 };
 }
 
@@ -138,6 +139,7 @@ void StepExecutor::record_step(const void* x, const long long* y, float* loss_sn
     th.params = cfg_.params; th.momentum = cfg_.momentum; th.step = cfg_.step_counter; th.aux = cfg_.aux;
     th.loss_acc = cfg_.loss_acc; th.loss_snapshot = loss_snapshot; th.ticket = cfg_.ticket;
     th.lr = cfg_.lr; th.mu = cfg_.mu; th.scale = 1.f / cfg_.world; th.rank = cfg_.rank; th.world = cfg_.world;
+    th.wire_bf16 = cfg_.wire_bf16;
     tp = &th;
   }
   int rc = cfg_.cluster > 1
@@ -157,7 +159,7 @@ void StepExecutor::record_step(const void* x, const long long* y, float* loss_sn
     std::memcpy(ib.p, cfg_.inbox_ptrs, sizeof(ib.p));
     rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
                                   cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
-                                  cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, compute_);
+                                  cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, cfg_.wire_bf16, compute_);
   }
   if ((rc != 0 || rc2 != 0) && err_.empty())
     err_ = std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(rc ? rc : rc2));

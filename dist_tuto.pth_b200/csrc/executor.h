@@ -31,6 +31,7 @@ struct StepConfig {
   float* aux;                        // conv2.weight in the kernels' smem layouts (maintained by the SGD kernel)
   void* inbox_ptrs[8];               // push exchange (sgd.cu): every rank's inbox
   int push;
+  int wire_bf16;                     // push exchange: bf16 on the wire
   int fused_tail;                    // gradient exchange + SGD in the tail of the step kernel (one kernel per step)
   unsigned int* ticket;              // device scratch of the fused tail
 };

@@ -167,8 +167,9 @@ extern "C" {
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, cudaStream_t stream) {
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream) {
   b2::SgdArgs a;
+  a.wire_bf16 = wire_bf16;
   a.loss_acc = loss_acc; a.loss_snapshot = (loss_acc != nullptr) ? loss_snapshot : nullptr;
   memset(&a.inbox, 0, sizeof(a.inbox));
   // push ("LL") exchange: needs an inbox on every rank, the double-buffered buckets and the device step counter (its epoch)

@@ -21,6 +21,9 @@ struct SgdArgs {
   long long grad_stride;     // > 0: two buckets, this step's bucket = step & 1; the OTHER bucket is re-zeroed here
   float* aux;                // optional [w2f 5000 | w2b 8000]: conv2.weight re-arranged for the forward/backward kernels
   PeerPtrs inbox;            // push variant only: every rank's inbox  [2 parities][world sources][n_vec][2 lines of 16 B]
+  int wire_bf16;             // push variant: gradients cross NVLink as bf16 (ONE 16-byte line {2 x bf16x2 + 2 flags} per float4 vector
+                             // instead of two), fp32 accumulation and fp32 master weights; every rank -- the sender included --
+                             // sums the same rounded values, so replicas stay bit-identical
   const float* loss_acc;     // optional: the step kernels' running [sum of batch-mean nll, #correct] ...
   float* loss_snapshot;      // ... copied here (2 floats) = the cumulative loss as of THIS step (per-step D2H source)
 };
@@ -65,7 +68,44 @@ __device__ __forceinline__ void exchange_apply_vec(const SgdArgs& a, size_t v, u
   const size_t cur_off = par * (size_t)a.grad_stride * sizeof(float);
   const uint4 mine = ld_cg_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.grads.p[rank]) + cur_off) + v);
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (world > 1) {
+  if (world > 1 && a.wire_bf16) {
+    // one line per vector: {bf16(x),bf16(y) | flag | bf16(z),bf16(w) | flag}
+    const uint32_t lo = pack_bf16x2(__uint_as_float(mine.x), __uint_as_float(mine.y));
+    const uint32_t hi = pack_bf16x2(__uint_as_float(mine.z), __uint_as_float(mine.w));
+    const uint4 l0 = make_uint4(lo, epoch, hi, epoch);
+    const size_t dst_line = (ipar * (size_t)world + (size_t)rank) * a.n_vec + v;
+#pragma unroll
+    for (int i = 1; i < B2_MAX_RANKS; ++i) {
+      if (i < world) {
+        int r = rank + i;
+        if (r >= world) r -= world;
+        st_volatile_v4(reinterpret_cast<uint4*>(a.inbox.p[r]) + dst_line, l0);
+      }
+    }
+    const uint4* in = reinterpret_cast<const uint4*>(a.inbox.p[rank]);
+#pragma unroll
+    for (int r = 0; r < B2_MAX_RANKS; ++r) {
+      if (r < world) {
+        uint4 q0;
+        if (r == rank) {
+          q0 = l0;
+        } else {
+          const uint4* src = in + (ipar * (size_t)world + (size_t)r) * a.n_vec + v;
+          unsigned long long spins = 0;
+          for (;;) {
+            q0 = ld_volatile_v4(src);
+            if (q0.y == epoch && q0.w == epoch) break;
+            if (++spins > B2_SPIN_LIMIT) {
+              printf("[b200dist] push all-reduce (bf16 wire): rank %d timed out waiting for rank %d (step %llu, vector %llu)\n", rank, r,
+                     st, (unsigned long long)v);
+              __trap();
+            }
+          }
+        }
+        g.x += bf16lo(q0.x); g.y += bf16hi(q0.x); g.z += bf16lo(q0.z); g.w += bf16hi(q0.z);
+      }
+    }
+  } else if (world > 1) {
     const size_t dst_line = ((ipar * (size_t)world + (size_t)rank) * a.n_vec + v) * 2;   // ((parity * world + source) * n_vec + v) * 2
     const uint4 l0 = make_uint4(mine.x, epoch, mine.y, epoch), l1 = make_uint4(mine.z, epoch, mine.w, epoch);
 #pragma unroll

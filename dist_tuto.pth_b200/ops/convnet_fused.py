@@ -119,11 +119,19 @@ class FusedTrainer:
     def __init__(self, bsz: int, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234, device=None,
                  p_drop: float = 0.5, group=None, raw_uint8: bool = False, num_slots: int = 4,
                  use_graph: bool = True, init_from: Optional[Net] = None, cluster: Optional[int] = None,
-                 deterministic: bool = False):
+                 deterministic: bool = False, grad_wire: Optional[torch.dtype] = None):
         self.C = _ext.C()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.bsz, self.lr, self.mu, self.seed, self.p_drop = int(bsz), float(lr), float(momentum), int(seed), p_drop
         self.group = group
+        # grad_wire=torch.bfloat16: the push exchange sends the locally reduced gradients as bf16 (one 16-byte line per
+        # float4 instead of two: half the NVLink bytes, stores and polling loads); accumulation and master weights stay fp32
+        # and all ranks sum the same rounded values, so replicas remain bit-identical (BASELINE config #2 "bf16 <-> fp32 cast").
+        if grad_wire is None and os.environ.get("B200DIST_WIRE", "").lower() == "bf16":
+            grad_wire = torch.bfloat16
+        if grad_wire not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("grad_wire must be None/float32 or bfloat16")
+        self.wire_bf16 = grad_wire == torch.bfloat16
         self.world = comm.get_world_size(group)
         self.rank = comm.group_ranks(group).index(comm.get_rank()) if comm.is_initialized() else 0
         self.raw_uint8 = raw_uint8
@@ -232,7 +240,7 @@ class FusedTrainer:
         cl = self.cluster if B * self.cluster <= 148 else 1
         if self.fused_tail and B * cl <= 128:       # the tail's grid-wide check-in needs every CTA resident
             tail = (self._grad_ptrs, self._inbox_ptrs, self.momentum, self.lr, self.mu, 1.0 / self.world, self.rank, self.world,
-                    self.ticket, None)
+                    self.ticket, None, self.wire_bf16)
             self.C.convnet_step(self.params, self.grads, x, y, self.loss_acc, None, None, self.step_counter, self.seed,
                                 self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux, tail)
             return
@@ -246,7 +254,7 @@ class FusedTrainer:
                                 self.rank * self.bsz, self.training, 1.0 / B, self.p_drop, 0, self.grad_stride, cl, self.aux)
         self.C.allreduce_sgd(self._grad_ptrs, self._sig_ptrs, self.params, self.momentum, self.step_counter,
                              self.lr, self.mu, 1.0 / self.world, self.rank, self.world, True, self.grad_stride,
-                             self.done_counter, self.aux, self._inbox_ptrs)
+                             self.done_counter, self.aux, self._inbox_ptrs, self.wire_bf16)
 
     def _warm(self):
         # forward-only launch: sets the kernel's dynamic-smem attribute outside of graph capture
@@ -372,7 +380,7 @@ class FusedTrainer:
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
                                       self.grad_stride, self.lr, self.mu, self.p_drop, max(1, loader.num_buffers - 2),
                                       self.cluster, self.aux, chunk, self._inbox_ptrs, loss_hist,
-                                      self.fused_tail and self.bsz * self.cluster <= 128, self.ticket),
+                                      self.fused_tail and self.bsz * self.cluster <= 128, self.ticket, self.wire_bf16),
                   self.training)
             self.exec_chunk = chunk
             self._executors[id(loader)] = ex

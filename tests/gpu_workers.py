@@ -439,3 +439,53 @@ def w_batched_trainer(rank, size):
     dist.broadcast(other, src=0)
     assert torch.equal(mine, other)
     dist.barrier()
+
+
+def w_bf16_wire_exchange(rank, size):
+    """FusedTrainer(grad_wire=bf16): same training curve as the fp32 wire within bf16 rounding of the exchanged gradients,
+    replicas still bit-identical, through both the Python graph path and the C++ executor."""
+    dev = _dev()
+    from dist_tuto.pth_b200 import data as D
+    from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
+    bsz = 16
+    ds = D.SyntheticMNIST(n=bsz * size * 10, seed=4)
+    idx = list(range(rank, len(ds), size))
+    out = {}
+    for wire in (None, torch.bfloat16):
+        tr = FusedTrainer(bsz, lr=0.05, seed=11, device=dev, p_drop=0.0, raw_uint8=True, grad_wire=wire)
+        assert tr.wire_bf16 == (wire is not None)
+        for i in range(9):
+            g = torch.Generator().manual_seed(70 + i * size + rank)
+            tr.step(torch.randint(0, 255, (bsz, 1, 28, 28), generator=g, dtype=torch.uint8).pin_memory(),
+                    torch.randint(0, 10, (bsz,), generator=g).pin_memory())
+        tr.sync_lag(0)
+        loader = D.NativeBatchLoader(D.Partition(ds, idx), bsz, seed=3, raw_uint8=True, pin_memory=True)
+        done, _ = tr.run_native(loader)
+        assert done == 10
+        torch.cuda.synchronize()
+        mine = tr.params.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other), "replicas differ with wire %s" % wire
+        out[wire] = (mine, tr.pop_loss_sum())
+        del tr
+    a, b = out[None], out[torch.bfloat16]
+    rel = float((a[0] - b[0]).norm() / a[0].norm())
+    assert rel < 2e-3, rel                       # 19 steps of lr 0.05 with gradients rounded to 8 mantissa bits
+    assert abs(a[1] - b[1]) < 2e-2 * abs(a[1]), (a[1], b[1])
+    dist.barrier()
+
+
+def w_suite_world(rank, size):
+    """Every multi-GPU worker in ONE launch (process start-up dominates on an 8-GPU box: 13 launches would cost minutes)."""
+    import time
+    t0 = time.time()
+    for fn in (w_symm_allreduce, w_average_gradients_gpu, w_fused_trainer, w_p2p_ring_gpu, w_push_exchange_equals_barrier_exchange,
+               w_bf16_wire_exchange, w_batched_trainer, w_train_fused_e2e, w_train_torch_engine_gpu, w_flag_reuse_stress,
+               w_large_sizes_vs_nccl):
+        t1 = time.time()
+        fn(rank, size)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print(f"SUITE world={size} {fn.__name__} ok in {time.time() - t1:.1f}s (total {time.time() - t0:.1f}s)", flush=True)

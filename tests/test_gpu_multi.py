@@ -45,6 +45,10 @@ def test_train_loop_torch_engine_symmetric_bucket_and_flat_sgd():
     go(W.w_train_torch_engine_gpu)
 
 
+def test_bf16_wire_exchange_tracks_fp32_wire():
+    go(W.w_bf16_wire_exchange)
+
+
 def test_batched_tensor_core_trainer_equals_global_batch_sgd():
     go(W.w_batched_trainer)
 
@@ -67,3 +71,8 @@ def test_flag_reuse_stress_1e5():
 
 def test_large_messages_vs_nccl_to_1gib():
     go(W.w_large_sizes_vs_nccl)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 8, reason="the one-launch suite is for the 8-GPU box")
+def test_world8_suite_one_launch():
+    go(W.w_suite_world, size=8)
