@@ -26,7 +26,7 @@ def newest(stem):
 def main():
     os.makedirs(OUT, exist_ok=True)
     lines = ["# SASS evidence (cuobjdump -sass of the objects linked into dist_tuto.pth_b200/_C.so, sm_100a) -- mnemonic counts per file"]
-    for stem in ("allreduce", "sgd", "convnet", "convnet_cluster", "gemm_tcgen05"):
+    for stem in ("allreduce", "sgd", "convnet", "convnet_cluster", "gemm_tcgen05", "convnet_batched"):
         obj = newest(stem)
         if obj is None:
             continue

@@ -68,25 +68,33 @@ def test_ddp_buckets_partition_the_parameters_in_reverse_order(shape_list, cap):
     ddp.remove_hooks()
 
 
-def test_all_reduce_variant_table_matches_the_measured_thresholds():
-    """pick_variant(): the size -> kernel table measured on B200 (profiles/n2, profiles/n8), checked without a GPU."""
+def test_all_reduce_variant_selection_follows_the_threshold_table():
+    """pick_variant(): size -> kernel from (ll_max, oneshot_max, nvls_min) -- the per-world thresholds that
+    bench/allreduce_sweep.py --emit-table measures (parallel/allreduce_table.json) -- checked without a GPU."""
     from dist_tuto.pth_b200.parallel.symm import SymmWorld, VARIANTS
 
-    def world(n, multicast):
+    def world(n, multicast, ll_max, oneshot_max, nvls_min):
         w = SymmWorld.__new__(SymmWorld)
         w.world, w.multicast = n, multicast
-        w.oneshot_max = (64 << 10) if n <= 2 else (8 << 10)
-        w.nvls_min = (1 << 62) if n <= 2 else (8 << 10) + 1
+        w.ll_max, w.oneshot_max, w.nvls_min = ll_max, oneshot_max, nvls_min
         return w
 
-    one, two, nvls = VARIANTS["oneshot"], VARIANTS["twoshot"], VARIANTS["nvls"]
-    assert world(1, False).pick_variant(1 << 20) == one
-    w2 = world(2, True)
-    assert [w2.pick_variant(b) for b in (1 << 10, 64 << 10, (64 << 10) + 16, 1 << 30)] == [one, one, two, two]   # NVLS never at 2
-    w8 = world(8, True)
-    assert [w8.pick_variant(b) for b in (1 << 10, 8 << 10, (8 << 10) + 16, 87360, 1 << 30)] == [one, one, nvls, nvls, nvls]
-    w8n = world(8, False)                                   # switch without multicast objects: two-shot takes over
-    assert [w8n.pick_variant(b) for b in (1 << 10, 87360, 1 << 30)] == [one, two, two]
+    one, two, nvls, ll = VARIANTS["oneshot"], VARIANTS["twoshot"], VARIANTS["nvls"], VARIANTS["ll"]
+    assert world(1, False, 0, 0, 0).pick_variant(1 << 20) == one
+    # the 2-GPU sweep of round 2 (profiles/n2): LL wins to 64 KB, one-shot to 1 MB, two-shot above; NVLS never pays at 2
+    w2 = world(2, True, 64 << 10, 1 << 20, 1 << 62)
+    assert [w2.pick_variant(b) for b in (1 << 10, 64 << 10, (64 << 10) + 16, 1 << 20, (1 << 20) + 16, 1 << 30)] == [ll, ll, one, one, two, two]
+    w8 = world(8, True, 32 << 10, 32 << 10, (32 << 10) + 1)
+    assert [w8.pick_variant(b) for b in (1 << 10, 32 << 10, (32 << 10) + 16, 87360, 1 << 30)] == [ll, ll, nvls, nvls, nvls]
+    w8n = world(8, False, 32 << 10, 32 << 10, (32 << 10) + 1)       # switch without multicast objects: two-shot takes over
+    assert [w8n.pick_variant(b) for b in (1 << 10, 87360, 1 << 30)] == [ll, two, two]
+    # the packaged table is well-formed and every entry is usable
+    import json
+    import os
+    from dist_tuto.pth_b200.parallel import symm
+    t = json.load(open(symm._TABLE_PATH))
+    for k, v in t["worlds"].items():
+        assert 2 <= int(k) <= 8 and set(v) >= {"ll_max", "oneshot_max", "nvls_min"} and v["ll_max"] <= symm.LL_CAP_VEC * 16
 
 
 def test_bf16_gradient_bucket_for_fp32_master_weights():

@@ -54,3 +54,29 @@ def test_cluster_policy_keeps_one_wave():
     # one CTA per sample above 64 samples, clusters below; C * B never exceeds the 148 SMs of a B200
     for b, c in ((128, 1), (64, 2), (32, 4), (16, 4), (8, 8), (1, 8)):
         assert cf.pick_cluster(b) == c and b * c <= 148
+
+
+def test_tc_layout_model_swizzles_are_involutions_and_window_addresses_stay_inside_the_image():
+    """ops/tc_layouts.py (host model of the TMA / UMMA shared-memory images used by csrc/convnet_batched.cu)."""
+    import numpy as np
+    from dist_tuto.pth_b200.ops import tc_layouts as L
+    # 32B / 128B swizzles permute 16-byte chunks inside their repeat (256 B / 1024 B) and are their own inverse
+    offs = [L.sw32_offset(r, c) for r in range(16) for c in (0, 16)]
+    assert sorted(offs) == list(range(0, 512, 16))
+    offs = [L.sw128_offset(r, c * 16) for r in range(8) for c in range(8)]
+    assert sorted(offs) == list(range(0, 1024, 16))
+    m = np.arange(64 * 16, dtype=np.uint16).reshape(64, 16)
+    assert np.array_equal(L.image_rows32(m), L.expected_tma_image_sw32(m))
+    # conv2-forward window descriptors: image [12 y][2 b][12 x] pixels of 32 B; tap (ky, kx) starts at ky*768 + kx*32 and walks
+    # 16 row groups (oy, b) 384 B apart, 8 pixels each -> the last byte touched is exactly the end of the 9216-byte image
+    last = max(ky * 768 + kx * 32 + g * 384 + ox * 32 + 31 for ky in range(5) for kx in range(5) for g in range(16) for ox in range(8))
+    assert last == 12 * 2 * 12 * 32 - 1
+    # conv2 weight-gradient windows: image [12 y][12 x] pixels; atoms kx = 0..7 (5 real), K-steps of two image rows;
+    # the over-read past the 4608-byte image stays inside the 512-byte zero padding the kernel keeps behind it
+    last = max(ky * 384 + ks * 768 + katom * 384 + pos * 32 + kx * 32 + 31
+               for ky in range(5) for ks in range(4) for katom in range(2) for pos in range(8) for kx in range(8))
+    assert 4608 <= last < 4608 + 512
+    # descriptor fields
+    d = L.smem_desc(0x1230, 32, 384, 6)
+    assert d & 0x3FFF == 0x123 and (d >> 16) & 0x3FFF == 2 and (d >> 32) & 0x3FFF == 24 and (d >> 61) == 6 and (d >> 46) & 3 == 1
+    assert L.idesc_bf16(128, 32, a_mn=1) == (1 << 4) | (1 << 7) | (1 << 10) | (1 << 15) | (4 << 17) | (8 << 24)
