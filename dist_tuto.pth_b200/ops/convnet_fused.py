@@ -127,7 +127,13 @@ class FusedTrainer:
         # grad_wire=torch.bfloat16: the push exchange sends the locally reduced gradients as bf16 (one 16-byte line per
         # float4 instead of two: half the NVLink bytes, stores and polling loads); accumulation and master weights stay fp32
         # and all ranks sum the same rounded values, so replicas remain bit-identical (BASELINE config #2 "bf16 <-> fp32 cast").
-        if grad_wire is None and os.environ.get("B200DIST_WIRE", "").lower() == "bf16":
+        env_wire = os.environ.get("B200DIST_WIRE", "").lower()
+        if grad_wire is None and env_wire in ("bf16", "fp32"):
+            grad_wire = torch.bfloat16 if env_wire == "bf16" else torch.float32
+        if grad_wire is None and comm.get_world_size(group) >= 4:
+            # measured at 8 GPUs, global batch 128 (profiles/n8/): 28.6 us/step with fp32 lines, 25.2 us with bf16 lines -- the
+            # exchange is what separates 8 GPUs from 1, so from 4 ranks up the wire is bf16 by default (BASELINE config #2:
+            # "fused ... bf16 <-> fp32 cast"); pass grad_wire=torch.float32 for an exact fp32 exchange
             grad_wire = torch.bfloat16
         if grad_wire not in (None, torch.float32, torch.bfloat16):
             raise ValueError("grad_wire must be None/float32 or bfloat16")
@@ -364,12 +370,13 @@ class FusedTrainer:
             if loader.batch_size != self.bsz:
                 raise ValueError("loader batch size != trainer batch size")
             block = (int(loader._l.block_bytes()) + 255) // 256 * 256
-            # Default: per-step issue with plain PDL stream launches (csrc/executor.cpp "direct mode"): measured on B200 that is
-            # the fastest way to feed the GPU (profiles/e2e_executor.json: 31 us/step with a graph per step, ~28 us/step device
-            # time; K-step chunk graphs pay ~3-6 us of device time per graph node at every boundary and came out SLOWER:
-            # 34.7 us/step at K = 8).  B200DIST_EXEC_CHUNK=K (2..8) selects the chunk pipeline anyway.
+            # Default: chunks of K = ring/3 (<= 8) steps, every kernel a plain PDL stream launch ("direct mode",
+            # csrc/executor.cpp): the chunk amortises the cross-stream events -- ~5 driver calls per step instead of 13,
+            # which matters when 8 ranks share the box's CPU quota -- while the device sees one unbroken kernel chain.
+            # (K-step chunk GRAPHS, B200DIST_EXEC_DIRECT=0, pay device time per graph node at every boundary and measured
+            # slower: profiles/e2e/executor_variants_r2.json.)  B200DIST_EXEC_CHUNK=1 issues step by step.
             env = os.environ.get("B200DIST_EXEC_CHUNK")
-            chunk = int(env) if env is not None else 1
+            chunk = int(env) if env is not None else loader.num_buffers // 3
             chunk = max(1, min(8, chunk))
             while chunk > 1 and loader.num_buffers < 3 * chunk:
                 chunk -= 1

@@ -76,3 +76,8 @@ def test_large_messages_vs_nccl_to_1gib():
 @pytest.mark.skipif(torch.cuda.device_count() < 8, reason="the one-launch suite is for the 8-GPU box")
 def test_world8_suite_one_launch():
     go(W.w_suite_world, size=8)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 8, reason="the one-launch suite is for the 8-GPU box")
+def test_world8_suite_rest_one_launch():
+    go(W.w_suite_world_rest, size=8)
