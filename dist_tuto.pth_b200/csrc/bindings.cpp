@@ -185,10 +185,15 @@ struct ExecutorPy {
     TORCH_CHECK(raw_u8 == l.impl->raw(), "loader / trainer input dtype mismatch");
     const size_t block = (l.impl->block_bytes() + 255) / 256 * 256;
     chunk = std::max(1, std::min(chunk, 8));
-    const size_t nblk = (size_t)std::max(2, 2 * chunk);
+    const size_t base_blk = (size_t)std::max(2, 2 * chunk);
+    // when the caller provides room for one block per loader slot behind the chunk blocks, the per-step path uses them
+    const size_t ring = (size_t)l.impl->num_slots();
+    const bool per_slot = (size_t)in_dev.numel() >= (base_blk + ring) * block && (size_t)loss_hist.numel() >= 2 * (base_blk + ring) &&
+                          base_blk + ring <= 96;
+    const size_t nblk = per_slot ? base_blk + ring : base_blk;
     TORCH_CHECK(in_dev.is_cuda() && in_dev.scalar_type() == torch::kUInt8 && (size_t)in_dev.numel() >= nblk * block,
                 "in_dev: CUDA uint8 buffer of >= max(2, 2 * chunk) * block bytes");
-    TORCH_CHECK(loss_hist.is_cuda() && loss_hist.scalar_type() == torch::kFloat32 && loss_hist.numel() >= 4 * chunk,
+    TORCH_CHECK(loss_hist.is_cuda() && loss_hist.scalar_type() == torch::kFloat32 && (size_t)loss_hist.numel() >= 2 * base_blk,
                 "loss_hist: CUDA fp32 [2 * chunk, 2]");
     b2::StepConfig c;
     std::memset(&c, 0, sizeof(c));
@@ -200,6 +205,7 @@ struct ExecutorPy {
     c.loss_acc = loss_acc.data_ptr<float>();
     for (size_t i = 0; i < nblk; ++i) c.in_dev[i] = in_dev.data_ptr<uint8_t>() + i * block;
     c.loss_hist = loss_hist.data_ptr<float>();
+    c.ring_base = per_slot ? (int)base_blk : 0;
     c.chunk = chunk;
     c.B = (int)l.impl->batch(); c.x_u8 = raw_u8; c.training = training;
     c.rank = rank; c.world = world; c.seed = seed; c.sample_base = sample_base; c.grad_stride = grad_stride;

@@ -20,9 +20,11 @@ struct StepConfig {
   unsigned long long* step_counter;
   unsigned int* done_counter;
   float* loss_acc;                   // [2]
-  unsigned char* in_dev[16];         // device input blocks, same layout as a loader slot: [x | pad | y]; [0..1] double-buffer
-                                     // the per-step path, [g*chunk .. g*chunk+chunk) are the blocks of chunk group g (0/1)
-  float* loss_hist;                  // device [2*chunk][2]: cumulative loss as of each step of a chunk (written by the SGD kernel)
+  unsigned char* in_dev[96];         // device input blocks, same layout as a loader slot: [x | pad | y]; [0..1] double-buffer
+                                     // the per-step path, [g*chunk .. g*chunk+chunk) are the blocks of chunk group g (0/1);
+                                     // [ring_base + slot] (when ring_base > 0): one block per loader slot for the per-step path
+  int ring_base;                     // 0: per-step path double-buffers blocks 0/1; > 0: per-slot blocks start here
+  float* loss_hist;                  // device [n blocks][2], same indexing as in_dev; originally [2*chunk][2]: cumulative loss as of each step of a chunk (written by the SGD kernel)
   int chunk;                         // steps per chunk (0/1 = per-step launches only), <= 8
   int B, x_u8, training, rank, world, cluster;
   unsigned long long seed;

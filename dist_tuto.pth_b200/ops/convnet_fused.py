@@ -370,18 +370,19 @@ class FusedTrainer:
             if loader.batch_size != self.bsz:
                 raise ValueError("loader batch size != trainer batch size")
             block = (int(loader._l.block_bytes()) + 255) // 256 * 256
-            # Default: chunks of K = ring/3 (<= 8) steps, every kernel a plain PDL stream launch ("direct mode",
-            # csrc/executor.cpp): the chunk amortises the cross-stream events -- ~5 driver calls per step instead of 13,
-            # which matters when 8 ranks share the box's CPU quota -- while the device sees one unbroken kernel chain.
-            # (K-step chunk GRAPHS, B200DIST_EXEC_DIRECT=0, pay device time per graph node at every boundary and measured
-            # slower: profiles/e2e/executor_variants_r2.json.)  B200DIST_EXEC_CHUNK=1 issues step by step.
+            # Default: step by step, every kernel a plain PDL stream launch ("direct mode", csrc/executor.cpp), one device
+            # block + loss-snapshot slot per loader slot (9 driver calls per step).  Measured alternatives, all slower at the
+            # driver's 20-step window (profiles/e2e/): a graph per step, K-step chunk graphs (device time per graph node at every
+            # boundary), K-step direct chunks (B200DIST_EXEC_CHUNK=K: fewer calls, but the first kernel of a chunk waits for
+            # all K copies -- 3.1 M vs 3.6 M samples/s at 1 GPU).
             env = os.environ.get("B200DIST_EXEC_CHUNK")
-            chunk = int(env) if env is not None else loader.num_buffers // 3
+            chunk = int(env) if env is not None else 1
             chunk = max(1, min(8, chunk))
             while chunk > 1 and loader.num_buffers < 3 * chunk:
                 chunk -= 1
-            in_dev = torch.zeros(max(2, 2 * chunk) * block, dtype=torch.uint8, device=self.device)
-            loss_hist = torch.zeros(4 * max(1, chunk), dtype=torch.float32, device=self.device)
+            nblk = max(2, 2 * chunk) + loader.num_buffers          # chunk blocks + one block per loader slot
+            in_dev = torch.zeros(nblk * block, dtype=torch.uint8, device=self.device)
+            loss_hist = torch.zeros(2 * nblk, dtype=torch.float32, device=self.device)
             ex = (self.C.StepExecutor(loader._l, self.params, self.momentum, self.grads, self._grad_ptrs, self._sig_ptrs,
                                       self.step_counter, self.done_counter, self.loss_acc, in_dev, self.raw_uint8,
                                       self.training, self.rank, self.world, self.seed, self.rank * self.bsz,
