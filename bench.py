@@ -42,6 +42,15 @@ def parse():
     return ap.parse_args()
 
 
+def gpu_smi_id(torch, dev):
+    """What to pass to ``nvidia-smi --id=``: the device's UUID (robust against CUDA_VISIBLE_DEVICES), else its index."""
+    try:
+        u = str(torch.cuda.get_device_properties(dev).uuid)
+        return u if u.startswith("GPU-") else "GPU-" + u
+    except Exception:
+        return dev.index
+
+
 def large_batch_arm(torch, b2, LB, rank, size, dev, max_over_ranks, steps=12):
     """Device-timed samples/s of full training steps at per-GPU batch ``LB`` (weak scaling) on the batched tcgen05 engine."""
     from dist_tuto.pth_b200.ops.convnet_batched import BatchedTrainer
@@ -141,7 +150,8 @@ def ours(args):
         b2.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(dev.index) as clk:
+        smi_id = gpu_smi_id(torch, dev)            # physical GPU (UUID): CUDA_VISIBLE_DEVICES re-numbers the logical index
+        with ClockSampler(smi_id) as clk:
             with torch.cuda.stream(st):
                 flush_buf.fill_(1)                                     # L2 flush: 256 MB > 126 MB L2
                 graphs[0].replay()                                     # pre-roll (untimed)
@@ -161,7 +171,7 @@ def ours(args):
             # the timed region (K x ~30 us) is shorter than one nvidia-smi query: sample the clocks under the SAME load by
             # replaying the timed graphs for ~0.6 s (not part of any reported time)
             reps = min(100000, max(8, int(600.0 / max(ms / K * G, 1e-3))))   # same count on every rank (ms is the max over ranks)
-            with ClockSampler(dev.index) as probe:
+            with ClockSampler(smi_id) as probe:
                 with torch.cuda.stream(st):
                     for s in range(reps):
                         graphs[s % n_graphs].replay()

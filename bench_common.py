@@ -21,6 +21,13 @@ class ClockSampler:
     """nvidia-smi SM clock + throttle-reason sampler running during the timed region."""
 
     def __init__(self, gpu_index=0, period_s=0.1):
+        if isinstance(gpu_index, int):      # logical CUDA index -> physical GPU (CUDA_VISIBLE_DEVICES re-numbers devices)
+            try:
+                import torch
+                u = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                gpu_index = u if u.startswith("GPU-") else "GPU-" + u
+            except Exception:
+                pass
         self.gpu, self.period, self.rows = gpu_index, period_s, []
         self._stop, self._th = threading.Event(), None
 
