@@ -497,6 +497,8 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
   }
 
   // ------------------------------------------------------------------ flush: only the gradient slices this CTA owns
+  __syncthreads();                                 // S8 of the last sample wrote s.g[W1..], s.g[B1..] from other warps (barrier (6) is
+                                                   // skipped after the last sample; racecheck: profiles/sanitize/r2_det_diag.txt)
   if (a.backward && cluster_id < a.B) {
     float* gdst = a.grads + (size_t)(step & 1ull) * (size_t)a.grad_stride;
     if (a.det_partials != nullptr) {               // deterministic mode: whole private slot per CTA (zeros outside its slices)
