@@ -213,13 +213,14 @@ def ours(args):
             t0 = time.perf_counter()
             advance(K)
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
-            ex = tr._executors[id(loader)][0]
-            host_stats = {k: (round(v, 1) if isinstance(v, float) else v) for k, v in ex.stats().items()}
-            exec_chunk = getattr(tr, "exec_chunk", 1) if ex.chunking() else 1
             torch.cuda.synchronize()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
             e2e = bsz * size * K / (e2e_ms / 1e3)
             assert seen == seen
+            ex = tr._executors[id(loader)][0]
+            host_stats = {k: (round(v, 1) if isinstance(v, float) else v) for k, v in ex.stats().items()}
+            host_stats["flag_mode"] = bool(ex.flag_mode())
+            exec_chunk = getattr(tr, "exec_chunk", 1) if ex.chunking() else 1
         # ------------------------------------------------------------ extra key: BASELINE.md B1 "large-batch variant"
         # Same network / optimizer / data-parallel exchange at a throughput-sized per-GPU batch (weak scaling), run by the
         # batched tensor-core engine (csrc/convnet_batched.cu).  Not the headline: `value` above stays global batch 128.
@@ -246,7 +247,9 @@ def ours(args):
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
                                                         "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "
                                                         + (f"chunks of {exec_chunk} steps = 3 graph launches on 3 streams ({exec_chunk} H2D nodes | {2 * exec_chunk} kernels | {exec_chunk} D2H nodes)"
-                                                           if exec_chunk > 1 else "one cudaGraphLaunch per step"),
+                                                           if exec_chunk > 1 else ("plain PDL stream launches; flag mode: stream memory ops instead of cross-stream events"
+                                                                                   if (not args.no_e2e and host_stats.get("flag_mode")) else
+                                                                                   "plain PDL stream launches, 3 streams ordered by events (9 driver calls per step)")),
                                             "e2e_host_us": host_stats if not args.no_e2e else None,
                                             "large_batch": large}),
                   flush=True)

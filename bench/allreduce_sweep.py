@@ -11,7 +11,8 @@ arm is measured twice in alternating order (A B .. B A) and the minimum kept, so
 Bandwidth columns:
   busbw   = 2(N-1)/N * bytes / t        the NCCL-tests convention (what a ring would push through each link)
   link_tx = bytes a GPU really sends:    two-shot (N-1)/N * bytes * 2 (gather slices + broadcast own slice);
-            NVLS  bytes/N * 2 ... see `link_bytes()`; reported as link_GBs = link_tx / t against 770 GB/s measured peer copy.
+            NVLS  bytes * (1 + 1/N) ... see `link_bytes()` (formulas checked against the NVLink counters, bench/nvlink_bytes.py);
+            reported as link_GBs = link_tx / t against 770 GB/s measured peer copy.
 ``--emit-table`` writes parallel/allreduce_table.json (per-world variant thresholds) from the measured winners.
 """
 import argparse
@@ -86,7 +87,10 @@ def body(rank, size):
     variants = [("ll", 3), ("oneshot", 0), ("twoshot", 1)] + ([("nvls", 2)] if w.multicast else [])
 
     def link_bytes(name, nbytes):
-        """Bytes one GPU transmits over its NVLink ports for one all-reduce of ``nbytes`` (receives the same)."""
+        """Bytes one GPU transmits over its NVLink ports for one all-reduce of ``nbytes`` (receives the same).  Checked against the
+        GPU's own link counters at 2 GPUs (bench/nvlink_bytes.py, profiles/n2/r2_nvlink_bytes_2gpu.json): one-shot 1.008x,
+        two-shot 1.002x and NVLS 1.000x of these formulas; the LL lines are 16-byte stores that the link carries at 32-byte
+        granularity, so LL really moves 1.8x the formula (3.6x the payload per peer) -- it is a latency variant."""
         if name == "ll":
             return 2 * nbytes * (size - 1)                       # 16-byte lines carry 8 data bytes, to every peer
         if name == "oneshot":
@@ -94,7 +98,9 @@ def body(rank, size):
         if name == "twoshot":
             return 2 * nbytes * (size - 1) / size                # peers read my slices + I push my reduced slice to them
         if name == "nvls":
-            return 2 * nbytes / size                             # my slice: one multimem.ld_reduce pull + one multimem.st push
+            # multimem.ld_reduce of slice j makes the switch fetch slice j from EVERY GPU (mine included, over my link): the N
+            # slices cost me nbytes of transmit; multimem.st of my reduced slice is one more nbytes / N (the switch replicates it)
+            return nbytes * (1 + 1.0 / size)
         return 2 * nbytes * (size - 1) / size                    # NCCL ring / tree: the bus-bandwidth convention
 
     for nbytes in sizes:

@@ -43,7 +43,8 @@ int b2_barrier_launch(const SignalPadsH* sig, int rank, int world, cudaStream_t 
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const SignalPadsH* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream);
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16,
+                            unsigned int* snap_flag, unsigned int snap_gen, cudaStream_t stream);
 int b2_sgd_flat_launch(float* p, float* m, const float* g, size_t n, float lr, float mu, float wd, int zero_grad,
                        cudaStream_t stream);
 size_t b2_convnet_smem_bytes();
@@ -52,14 +53,15 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const void* tail, float* det_partials, cudaStream_t stream);
+                           const void* tail, float* det_partials, const unsigned int* in_flag, unsigned int in_gen, cudaStream_t stream);
 int b2_det_reduce_launch(const float* partials, int n_slots, long long slot_stride, float* grads, const unsigned long long* step,
                          long long grad_stride, size_t n_elems, float* loss_acc, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const void* tail, float* det_partials, cudaStream_t stream);
+                              const float* aux, const void* tail, float* det_partials, const unsigned int* in_flag, unsigned int in_gen,
+                              cudaStream_t stream);
 void b2_convnet_set_tc(int on);
 int b2_convnet_get_tc();
 int b2_gemm_available();
@@ -224,6 +226,12 @@ struct ExecutorPy {
     }
     const int cap = std::max(1, l.impl->num_slots() - 2);
     c10::cuda::CUDAGuard guard(params.device());
+    if (per_slot) {      // generation words of the ring path's flag mode (executor.cpp)
+      torch::Tensor flags = torch::zeros({2 * (int64_t)ring}, torch::TensorOptions().dtype(torch::kInt32).device(params.device()));
+      c10::cuda::getCurrentCUDAStream().synchronize();
+      c.flags = reinterpret_cast<unsigned int*>(flags.data_ptr());
+      keep.push_back(flags);
+    }
     impl = std::make_unique<b2::StepExecutor>(c, l.impl.get(), std::min(max_in_flight, cap));
     if (!impl->prepare()) throw std::runtime_error("StepExecutor: " + impl->error());
   }
@@ -310,7 +318,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(params.device());
     ck_cuda(b2_allreduce_sgd_launch(&g, &s, params.data_ptr<float>(), momentum.data_ptr<float>(), st, (size_t)params.numel(),
                                     (float)lr, (float)mu, (float)scale, rank, world, zero_grads, grad_stride, dc, ax,
-                                    inbox.empty() ? nullptr : &ib, nullptr, nullptr, wire_bf16 ? 1 : 0, cur_stream()),
+                                    inbox.empty() ? nullptr : &ib, nullptr, nullptr, wire_bf16 ? 1 : 0, nullptr, 0u, cur_stream()),
             "allreduce_sgd launch");
   }, py::arg("grads"), py::arg("sigs"), py::arg("params"), py::arg("momentum"), py::arg("step"), py::arg("lr"), py::arg("mu"),
      py::arg("scale"), py::arg("rank"), py::arg("world"), py::arg("zero_grads"), py::arg("grad_stride") = 0,
@@ -394,12 +402,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       TORCH_CHECK(cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 1, 2, 4 or 8");
       ck_cuda(b2_convnet_cluster_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                         la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                        cluster, max_ctas, grad_stride, ax, tp, dp, cur_stream()), "convnet_cluster launch");
+                                        cluster, max_ctas, grad_stride, ax, tp, dp, nullptr, 0u, cur_stream()), "convnet_cluster launch");
       return;
     }
     ck_cuda(b2_convnet_step_launch(params.data_ptr<float>(), g, x.data_ptr(), u8, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
                                    la, lp, mo, st, seed, sample_base, B, training, g != nullptr, (float)inv_bsz, (float)p_drop,
-                                   max_ctas, grad_stride, ax, tp, dp, cur_stream()), "convnet_step launch");
+                                   max_ctas, grad_stride, ax, tp, dp, nullptr, 0u, cur_stream()), "convnet_step launch");
   }, py::arg("params"), py::arg("grads"), py::arg("x"), py::arg("target"), py::arg("loss_acc"), py::arg("out_logp"),
      py::arg("mask_out"), py::arg("step"), py::arg("seed"), py::arg("sample_base"), py::arg("training"), py::arg("inv_bsz"),
      py::arg("p_drop") = 0.5, py::arg("max_ctas") = 0, py::arg("grad_stride") = 0, py::arg("cluster") = 1, py::arg("aux") = py::none(),
@@ -540,6 +548,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("inbox") = std::vector<unsigned long long>(), py::arg("loss_hist") = torch::Tensor(), py::arg("fused_tail") = false,
            py::arg("ticket") = torch::Tensor(), py::arg("wire_bf16") = false, py::keep_alive<1, 2>())
       .def("chunking", [](ExecutorPy& e) { return e.impl->chunking(); })
+      .def("flag_mode", [](ExecutorPy& e) { return e.impl->flag_mode(); })
       .def("chunk_note", [](ExecutorPy& e) { return e.impl->chunk_note(); })
       .def("stats", [](ExecutorPy& e) {
         const auto& s = e.impl->stats();

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     for (int i = tid; i < NPAR / 4; i += T) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   b2::pdl_wait();                    // parameters / step counter written by the previous all-reduce+SGD kernel
+  if (tid == T - 1) wait_input(a);   // (executor path) the H2D copy of this step's batch; the barrier that ends staging publishes it
   {
     // all global loads are issued before their first use (one L2 round trip instead of a dependent chain)
     const bool fast = (a.aux != nullptr) && !TC;   // conv2.weight already in both smem layouts (written by sgd.cu)
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
     if (a.x_u8) {
       const uint4* xs = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * 784);
       if (tid < 49) {                              // 784 bytes = 49 x 16
-        const uint4 q = __ldg(xs + tid);
+        const uint4 q = __ldcg(xs + tid);
         const unsigned int wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 16; ++e)
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
       }
     } else {
       const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + (size_t)b * 784);
-      if (tid < 196) reinterpret_cast<float4*>(s.x)[tid] = __ldg(xs + tid);
+      if (tid < 196) reinterpret_cast<float4*>(s.x)[tid] = __ldcg(xs + tid);
     }
     if (tid >= 256 && tid < 274) {
       const int q = tid - 256;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(T, 1) convnet_step_kernel(Args a) {
 
     // -------------------------------------------------------------- S4: fc2 + log_softmax + nll
     if (tid < 32) {
-      const long long y = a.target[b];
+      const long long y = __ldcg(a.target + b);
       float logit = -INFINITY;
       if (tid < 10) {
         float acc = s.b4[tid];
@@ -757,7 +758,8 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const cn::FusedTailHost* tail, float* det_partials, cudaStream_t stream) {
+                           const cn::FusedTailHost* tail, float* det_partials, const unsigned int* in_flag, unsigned int in_gen,
+                           cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cn::Smem) + 1024;
   if (!configured) {
@@ -774,6 +776,7 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
   a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
   cn::fill_tail(a.tail, backward ? tail : nullptr, grad_stride);
   a.det_partials = backward ? det_partials : nullptr;
+  a.in_flag = in_flag; a.in_gen = in_gen;
   int grid = B;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;

@@ -38,7 +38,19 @@ struct Args {
   b2::FusedTail tail;       // enabled: gradient exchange + SGD run in the tail of THIS kernel (sgd_device.cuh)
   float* det_partials;      // deterministic mode: CTA i stores its gradient sums to det_partials + i * DET_STRIDE (plain
                             // stores) instead of red.add-ing into the bucket; det_reduce_kernel (sgd.cu) sums the slots in order
+  const unsigned int* in_flag;   // optional "this batch has landed" word: the executor's copy stream writes in_gen there with a
+  unsigned int in_gen;           // stream memory op right behind the H2D copy of x / target; the kernel polls it instead of the
+                                 // compute stream waiting on an event, so consecutive steps stay one unbroken PDL kernel chain
 };
+
+// Blocks the calling thread until the batch the kernel is about to read has landed (cyclic compare: generations wrap).
+__device__ __forceinline__ void wait_input(const Args& a) {
+  if (a.in_flag == nullptr) return;
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.in_flag) : "memory");
+  } while ((int)(v - a.in_gen) < 0);
+}
 constexpr int DET_STRIDE = 21888;   // = NPAR_ALLOC of ops/convnet_fused.py
 
 // Host-side description of the fused tail (C ABI of the launchers); nullptr / enabled == 0 -> two-kernel step.

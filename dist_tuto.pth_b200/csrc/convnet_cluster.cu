@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     for (int i = tid; i < NPAR / 4; i += T) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   b2::pdl_wait();
+  if (tid == T - 1) wait_input(a);   // (executor path) the H2D copy of this step's batch; the cluster barrier below publishes it
   {
     const bool fast = (a.aux != nullptr);   // conv2.weight already in both smem layouts (written by sgd.cu)
     float4 fa[3], fb[4];            // pre-arranged conv2.weight: every load is in flight before the first store
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
     if (a.x_u8) {
       const uint4* xs = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * 784);
       if (tid < 49) {
-        const uint4 q = __ldg(xs + tid);
+        const uint4 q = __ldcg(xs + tid);
         const unsigned int wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 16; ++e)
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
       }
     } else {
       const float4* xs = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + (size_t)b * 784);
-      if (tid < 196) reinterpret_cast<float4*>(s.x)[tid] = __ldg(xs + tid);
+      if (tid < 196) reinterpret_cast<float4*>(s.x)[tid] = __ldcg(xs + tid);
     }
     if (tid >= 256 && tid < 274) {
       const int q = tid - 256;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(T, 1) convnet_cluster_kernel(Args a) {
 
     // -------------------------------------------------------------- S4: fc2 + log_softmax + nll (redundant in every CTA)
     if (tid < 32) {
-      const long long y = a.target[b];
+      const long long y = __ldcg(a.target + b);
       float logit = -INFINITY;
       if (tid < 10) {
         float acc = s.b4[tid];
@@ -546,7 +547,8 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const cn::FusedTailHost* tail, float* det_partials, cudaStream_t stream) {
+                              const float* aux, const cn::FusedTailHost* tail, float* det_partials, const unsigned int* in_flag,
+                              unsigned int in_gen, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(cnc::Smem);
   if (!configured) {
@@ -563,6 +565,7 @@ int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, 
   a.mean = 0.1307f; a.inv_std = 1.f / 0.3081f; a.grad_stride = grad_stride; a.aux = aux;
   cn::fill_tail(a.tail, backward ? tail : nullptr, grad_stride);
   a.det_partials = backward ? det_partials : nullptr;
+  a.in_flag = in_flag; a.in_gen = in_gen;
   int clusters = B;
   if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
   if (clusters < 1) clusters = 1;

@@ -24,6 +24,8 @@
 // memory and its own D2H read-back; the per-step path remains for the steps that do not fill a chunk.
 #include "executor.h"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -34,18 +36,21 @@ int b2_convnet_step_launch(const float* params, float* grads, const void* x, int
                            float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                            unsigned long long seed, long long sample_base, int B, int training, int backward,
                            float inv_bsz, float p_drop, int max_ctas, long long grad_stride, const float* aux,
-                           const void* tail, float* det_partials, cudaStream_t stream);
+                           const void* tail, float* det_partials, const unsigned int* in_flag, unsigned int in_gen,
+                           cudaStream_t stream);
 struct PeerPtrsC { void* p[8]; };
 struct SignalPadsC { uint32_t* pad[8]; };
 int b2_allreduce_sgd_launch(const PeerPtrsC* grads, const SignalPadsC* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrsC* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream);
+                            const PeerPtrsC* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16,
+                            unsigned int* snap_flag, unsigned int snap_gen, cudaStream_t stream);
 int b2_convnet_cluster_launch(const float* params, float* grads, const void* x, int x_u8, const long long* target,
                               float* loss_acc, float* out_logp, float* mask_out, const unsigned long long* step,
                               unsigned long long seed, long long sample_base, int B, int training, int backward,
                               float inv_bsz, float p_drop, int cluster, int max_clusters, long long grad_stride,
-                              const float* aux, const void* tail, float* det_partials, cudaStream_t stream);
+                              const float* aux, const void* tail, float* det_partials, const unsigned int* in_flag,
+                              unsigned int in_gen, cudaStream_t stream);
 int b2_convnet_npar();
 struct FusedTailHostC {            // mirrors cn::FusedTailHost (csrc/convnet_args.cuh)
   void* grad_ptrs[8];
@@ -65,6 +70,22 @@ struct FusedTailHostC {            // mirrors cn::FusedTailHost (csrc/convnet_ar
 
 namespace b2 {
 
+// Stream memory operations (driver API, resolved at run time like csrc/symm_mem.cpp does): the copy stream publishes "batch
+// landed" words the step kernels poll, the D2H stream waits on the "loss snapshot written" word the optimizer kernel sets.
+using WriteValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+using WaitValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static void* drv_sym(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return fn;
+}
+static WriteValue32Fn p_write32() { static auto f = reinterpret_cast<WriteValue32Fn>(drv_sym("cuStreamWriteValue32")); return f; }
+static WaitValue32Fn p_wait32() { static auto f = reinterpret_cast<WaitValue32Fn>(drv_sym("cuStreamWaitValue32")); return f; }
+
 static inline long long now_ns() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -82,6 +103,22 @@ StepExecutor::StepExecutor(const StepConfig& cfg, NativeLoader* loader, int max_
   {
     const char* e = getenv("B200DIST_EXEC_DIRECT");
     direct_ = (e == nullptr || e[0] != '0');
+  }
+  {
+    // flag mode of the per-slot ring path: no cross-stream events at all (see run()); needs the stream memory operations.
+    // Opt-in (B200DIST_EXEC_FLAGS=1): measured NOT faster than the event path (profiles/e2e/executor_flag_mode_r2.json:
+    // 3.55 / 3.28 M vs 3.69 M samples/s at 20 steps, 3.96 M vs 4.06 M at 400) -- the event waits were not what separates
+    // the stream-launched steps (32 us) from the graph-replayed ones (28 us).
+    const char* e = getenv("B200DIST_EXEC_FLAGS");
+    flags_ = (e != nullptr && e[0] == '1') && direct_ && cfg_.ring_base > 0 && cfg_.flags != nullptr && !cfg_.fused_tail &&
+             cfg_.loss_hist != nullptr && p_write32() != nullptr && p_wait32() != nullptr;
+    if (flags_) {      // probe: some driver configurations refuse memory operations on a stream
+      if (p_write32()((CUstream)copy_, (CUdeviceptr)(uintptr_t)cfg_.flags, 0u, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS ||
+          cudaStreamSynchronize(copy_) != cudaSuccess) {
+        cudaGetLastError();
+        flags_ = false;
+      }
+    }
   }
   const int K = cfg_.chunk, nb = loader_->num_slots();
   chunk_ok_ = K >= 2 && K <= 8 && nb >= 3 * K && cfg_.loss_hist != nullptr;
@@ -129,7 +166,8 @@ StepExecutor::~StepExecutor() {
 }
 
 // Enqueues the two kernels of one step on the compute stream (called under stream capture).
-void StepExecutor::record_step(const void* x, const long long* y, float* loss_snapshot) {
+void StepExecutor::record_step(const void* x, const long long* y, float* loss_snapshot, const unsigned int* in_flag,
+                               unsigned int* snap_flag, unsigned int gen) {
   FusedTailHostC th;
   const void* tp = nullptr;
   if (cfg_.fused_tail) {
@@ -145,10 +183,10 @@ void StepExecutor::record_step(const void* x, const long long* y, float* loss_sn
   int rc = cfg_.cluster > 1
                ? b2_convnet_cluster_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                            cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1,
-                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, compute_)
+                                           1.f / cfg_.B, cfg_.p_drop, cfg_.cluster, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, in_flag, gen, compute_)
                : b2_convnet_step_launch(cfg_.params, cfg_.grads_local, x, cfg_.x_u8, y, cfg_.loss_acc, nullptr, nullptr,
                                         cfg_.step_counter, cfg_.seed, cfg_.sample_base, cfg_.B, cfg_.training, 1, 1.f / cfg_.B,
-                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, compute_);
+                                        cfg_.p_drop, 0, cfg_.grad_stride, cfg_.aux, tp, nullptr, in_flag, gen, compute_);
   int rc2 = 0;
   if (!cfg_.fused_tail) {
     PeerPtrsC g;
@@ -159,7 +197,8 @@ void StepExecutor::record_step(const void* x, const long long* y, float* loss_sn
     std::memcpy(ib.p, cfg_.inbox_ptrs, sizeof(ib.p));
     rc2 = b2_allreduce_sgd_launch(&g, &sg, cfg_.params, cfg_.momentum, cfg_.step_counter, (size_t)b2_convnet_npar(),
                                   cfg_.lr, cfg_.mu, 1.f / cfg_.world, cfg_.rank, cfg_.world, 1, cfg_.grad_stride,
-                                  cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, cfg_.wire_bf16, compute_);
+                                  cfg_.done_counter, cfg_.aux, cfg_.push ? &ib : nullptr, cfg_.loss_acc, loss_snapshot, cfg_.wire_bf16,
+                                  snap_flag, gen, compute_);
   }
   if ((rc != 0 || rc2 != 0) && err_.empty())
     err_ = std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(rc ? rc : rc2));
@@ -260,6 +299,9 @@ void StepExecutor::drain_copies() {
 void StepExecutor::drain() {
   drain_copies();
   while (!in_flight_.empty()) retire_oldest();
+  // flag mode retires a step when its loss snapshot has been read back, which the optimizer kernel allows as soon as it
+  // has started: wait for the kernels themselves before the caller touches parameters or another stream takes over
+  if (flags_) cudaStreamSynchronize(compute_);
 }
 
 int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending_count, int* epoch_done) {
@@ -360,6 +402,36 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
       // quota with up to 8 ranks: calls per step are what bounds the end-to-end rate at 8 GPUs).
       unsigned char* blk = cfg_.in_dev[cfg_.ring_base + slot];
       float* snap = cfg_.loss_hist + 2 * (cfg_.ring_base + slot);
+      if (flags_) {
+        // Flag mode (opt-in): NO cross-stream event.  copy stream: H2D, then a stream memory op writes this step's generation
+        // into the slot's "landed" word -- the step kernel polls it (convnet_args.cuh wait_input); compute stream: nothing but
+        // the kernels, so step k+1's kernel pre-launches behind step k's optimizer kernel exactly as inside one CUDA graph
+        // (an event wait between them cost ~3 us of device time per step); D2H stream: waits (stream memory op) for the
+        // "snapshot written" word the optimizer kernel sets, then reads the loss.  7 driver calls per step.
+        const unsigned int gen = (unsigned int)(issued_ + 1);
+        unsigned int* in_flag = cfg_.flags + 2 * slot;
+        unsigned int* snap_flag = cfg_.flags + 2 * slot + 1;
+        cudaMemcpyAsync(blk, loader_->slot(slot).x, loader_->block_bytes(), cudaMemcpyHostToDevice, copy_);
+        CUresult r1 = p_write32()((CUstream)copy_, (CUdeviceptr)(uintptr_t)in_flag, gen, CU_STREAM_WRITE_VALUE_DEFAULT);
+        err_.clear();
+        record_step(blk, reinterpret_cast<const long long*>(blk + loader_->y_offset()), snap, in_flag, snap_flag, gen);
+        CUresult r2 = p_wait32()((CUstream)d2h_, (CUdeviceptr)(uintptr_t)snap_flag, gen, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+          // without the write the kernel just launched would spin forever: publish the generation from the host side
+          if (r1 != CUDA_SUCCESS) { cudaStreamSynchronize(copy_); cudaMemcpy(in_flag, &gen, sizeof(gen), cudaMemcpyHostToDevice); }
+          if (err_.empty()) err_ = "stream memory operation failed (cuStreamWriteValue32 / cuStreamWaitValue32)";
+          cudaStreamSynchronize(compute_);
+          return -1;
+        }
+        if (!err_.empty()) return -1;
+        cudaMemcpyAsync(slots_[slot].loss_pin, snap, 2 * sizeof(float), cudaMemcpyDeviceToHost, d2h_);
+        cudaEventRecord(slots_[slot].done, d2h_);
+        in_flight_.push_back({slot, slot, false});
+        ++issued_;
+        ++done;
+        ++stats_.single_steps;
+        continue;
+      }
       cudaMemcpyAsync(blk, loader_->slot(slot).x, loader_->block_bytes(), cudaMemcpyHostToDevice, copy_);
       cudaEventRecord(copied_[p], copy_);
       cudaStreamWaitEvent(compute_, copied_[p], 0);

@@ -36,6 +36,8 @@ struct StepConfig {
   int wire_bf16;                     // push exchange: bf16 on the wire
   int fused_tail;                    // gradient exchange + SGD in the tail of the step kernel (one kernel per step)
   unsigned int* ticket;              // device scratch of the fused tail
+  unsigned int* flags;               // device [num_slots][2] zero-initialised words: {batch landed, loss snapshot written}
+                                     // generations of the per-slot ring path's flag mode (nullptr: event mode)
 };
 
 class StepExecutor {
@@ -51,6 +53,7 @@ class StepExecutor {
   double last_loss_cumulative() const { return last_loss_; }
   const std::string& error() const { return err_; }
   bool chunking() const { return chunk_ok_; }
+  bool flag_mode() const { return flags_; }
   // host-side time accounting of run() (ns): where the feeding loop waits -- {loader next(), copy-event waits, loss retire
   // waits, everything else (driver calls)}, and the number of chunked / single steps issued
   struct Stats { long long next_ns = 0, copy_wait_ns = 0, retire_ns = 0, total_ns = 0, chunk_steps = 0, single_steps = 0; };
@@ -67,7 +70,8 @@ class StepExecutor {
   bool capture_chunk(int g, int size_idx);
   void release_copied(bool block_for_one);
   void drain_copies();
-  void record_step(const void* x, const long long* y, float* loss_snapshot = nullptr);
+  void record_step(const void* x, const long long* y, float* loss_snapshot = nullptr, const unsigned int* in_flag = nullptr,
+                   unsigned int* snap_flag = nullptr, unsigned int gen = 0);
   void retire_oldest();
   StepConfig cfg_;
   NativeLoader* loader_;
@@ -76,6 +80,7 @@ class StepExecutor {
   cudaGraphExec_t exec_[2] = {nullptr, nullptr};     // the two kernels, reading in_dev[parity]
   cudaEvent_t copied_[2] = {nullptr, nullptr}, kernels_done_[2] = {nullptr, nullptr}, loss_read_[2] = {nullptr, nullptr};
   bool direct_ = true;                               // per-step path: plain PDL stream launches instead of a graph per step
+  bool flags_ = false;                               // per-slot ring path without cross-stream events (stream memory ops)
   std::vector<Slot> slots_;
   // chunk pipeline: K consecutive steps = three graph launches on three streams (see executor.cpp).  The slot of batch b is
   // b % num_slots, so the pinned addresses of a slot group are fixed; g = chunk parity selects the device block group.

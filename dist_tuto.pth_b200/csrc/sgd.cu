@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_kernel(SgdArgs a) {
     if (a.step != nullptr) seen = atomicAdd(a.done_counter, 1u);    // result is only consumed at the very end (latency hidden)
   }
   __syncthreads();
+  publish_snapshot(a);
   uint32_t epoch = 0;
   if (world > 1) {
     epoch = barrier_epoch_load(a.sig, rank);
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kSgdThreads) allreduce_sgd_push_kernel(SgdArgs
     seen = atomicAdd(a.done_counter, 1u);
   }
   __syncthreads();
+  publish_snapshot(a);
   const unsigned long long st = s_step;
   const size_t stride = (size_t)gridDim.x * kSgdThreads;
   for (size_t v = (size_t)blockIdx.x * kSgdThreads + threadIdx.x; v < a.n_vec; v += stride) exchange_apply_vec(a, v, st);
@@ -167,10 +169,12 @@ extern "C" {
 int b2_allreduce_sgd_launch(const PeerPtrs* grads, const b2::SignalPads* sig, float* params, float* momentum,
                             unsigned long long* step, size_t n_elems, float lr, float mu, float scale, int rank,
                             int world, int zero_grads, long long grad_stride, unsigned int* done_counter, float* aux,
-                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16, cudaStream_t stream) {
+                            const PeerPtrs* inbox, const float* loss_acc, float* loss_snapshot, int wire_bf16,
+                            unsigned int* snap_flag, unsigned int snap_gen, cudaStream_t stream) {
   b2::SgdArgs a;
   a.wire_bf16 = wire_bf16;
   a.loss_acc = loss_acc; a.loss_snapshot = (loss_acc != nullptr) ? loss_snapshot : nullptr;
+  a.snap_flag = (a.loss_snapshot != nullptr) ? snap_flag : nullptr; a.snap_gen = snap_gen;
   memset(&a.inbox, 0, sizeof(a.inbox));
   // push ("LL") exchange: needs an inbox on every rank, the double-buffered buckets and the device step counter (its epoch)
   const bool push = inbox != nullptr && world > 1;

@@ -193,12 +193,15 @@ def test_train_loop_single_gpu_fused(dev):
     assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
 
 
-@pytest.mark.parametrize("num_buffers,chunk", [(6, 4), (8, 2), (12, 4), (24, 8), (7, 2)])
-def test_native_executor_matches_python_loop(dev, num_buffers, chunk, monkeypatch):
-    """C++ StepExecutor (prefetch thread -> graph launches) == stepping the same loader from Python.
-    (6, 4): ring too shallow for chunks of 4 -> the Python side lowers K to 2; the others: K-step chunk pipeline (needs a
-    ring of >= 3K slots) + per-step path for what does not fill a chunk."""
+@pytest.mark.parametrize("num_buffers,chunk,flags", [(6, 4, 0), (8, 2, 0), (12, 4, 1), (24, 8, 0), (7, 2, 0), (8, 1, 1), (24, 1, 1),
+                                                     (24, 1, 0)])
+def test_native_executor_matches_python_loop(dev, num_buffers, chunk, flags, monkeypatch):
+    """C++ StepExecutor (prefetch thread -> kernel launches) == stepping the same loader from Python.
+    (6, 4): ring too shallow for chunks of 4 -> the Python side lowers K to 2; K >= 2: K-step chunk pipeline (needs a
+    ring of >= 3K slots) + per-step path for what does not fill a chunk; K = 1 (the default): per-slot ring path, with
+    (flags = 1, opt-in) the "batch landed" / "snapshot written" words instead of cross-stream events, or (0, default) events."""
     monkeypatch.setenv("B200DIST_EXEC_CHUNK", str(chunk))
+    monkeypatch.setenv("B200DIST_EXEC_FLAGS", str(flags))
     from dist_tuto.pth_b200 import data as D
     from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
     ds = D.SyntheticMNIST(n=1000, seed=2)                 # 1000 = 15 x 64 + 40 -> exercises the short tail batch
@@ -215,6 +218,7 @@ def test_native_executor_matches_python_loop(dev, num_buffers, chunk, monkeypatc
             while k_eff > 1 and max(4, num_buffers) < 3 * k_eff:
                 k_eff -= 1
             assert tr.exec_chunk == k_eff and ex.chunking() == (k_eff >= 2), ex.chunk_note()
+            assert ex.flag_mode() == bool(flags)
             done2, _ = tr.run_native(loader, max_steps=6)        # second epoch, budgeted: chunk (4) + 2 single steps
             assert done2 == 6
         else:
