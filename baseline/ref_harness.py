@@ -77,7 +77,7 @@ def run(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     sys.path.insert(0, ROOT)
-    from bench_common import ClockSampler, max_over_ranks, result_line, synthetic_idx_dir  # no kernels in there
+    from bench_common import ClockSampler, aligned_start, max_over_ranks, result_line, synthetic_idx_dir  # no kernels in there
 
     K, W = args.steps, args.warmup
     bsz = 128 // world                                              # train_dist.py:85
@@ -139,9 +139,7 @@ def run(args):
     for _ in range(W):
         d, t = next_batch()
         step(d.cuda(local), t.cuda(local)).item()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
+    t0 = aligned_start(dev)                      # barrier + synchronize + common start instant (same as our arm)
     h2d = 0
     for _ in range(K):
         d, t = next_batch()

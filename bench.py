@@ -100,7 +100,7 @@ def large_batch_arm(torch, b2, LB, rank, size, dev, max_over_ranks, steps=12):
 def ours(args):
     import torch
     import dist_tuto.pth_b200 as b2
-    from bench_common import ClockSampler, max_over_ranks, result_line
+    from bench_common import ClockSampler, aligned_start, max_over_ranks, result_line
     from dist_tuto.pth_b200.data import SyntheticMNIST
     from dist_tuto.pth_b200.ops.convnet_fused import FusedTrainer
 
@@ -207,10 +207,8 @@ def ours(args):
                     done += d
 
             advance(W)
-            b2.barrier()
-            torch.cuda.synchronize()
             tr._executors[id(loader)][0].reset_stats()
-            t0 = time.perf_counter()
+            t0 = aligned_start(dev)                      # barrier + synchronize, then all ranks leave at the same instant
             advance(K)
             seen = tr.last_loss_cumulative()             # host copy of the last step's D2H loss
             torch.cuda.synchronize()
@@ -242,7 +240,9 @@ def ours(args):
                                                                   else ("barrier + peer loads" if size > 1 else "none (1 GPU)")),
                                             "l2": l2_note,
                                             "timing": "CUDA events on the launch stream: [L2 flush][pre-roll graph, untimed] e0 [K steps] e1, "
-                                                      "enqueued back to back; max over ranks",
+                                                      "enqueued back to back; max over ranks.  e2e: host clock from a common start instant (barrier + "
+                                                      "synchronize, then all ranks spin to an agreed CLOCK_MONOTONIC time) to this rank's synchronize "
+                                                      "after its K-th loss read-back; max over ranks",
                                             "graph_chunk": G, "symm": sym,
                                             "e2e_path": "partition_dataset(raw_uint8) -> C++ prefetch thread -> C++ StepExecutor: per step one H2D "
                                                         "(uint8 batch + labels, pinned), 2 kernels, one D2H (loss); "

@@ -82,6 +82,34 @@ def max_over_ranks(value, device):
     return float(t.item())
 
 
+def aligned_start(device, lead_s=0.003):
+    """Barrier + synchronize, then every rank leaves at the same instant; returns that instant (``time.perf_counter()``).
+
+    A barrier alone lets the ranks go as each host thread happens to notice it (NCCL completion polling, Python): a skew
+    of 100+ us, which a 20-step window of ~30 us steps then reports as "step time" because the first gradient exchange
+    waits for the last rank to start.  All ranks of this single-node job share CLOCK_MONOTONIC (what perf_counter reads on
+    Linux), so they agree on a start time a few milliseconds ahead (MAX over ranks) and spin until it.  Used by both arms."""
+    import time
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    on_gpu = torch.cuda.is_available() and torch.device(device).type == "cuda"
+    if multi:
+        dist.barrier()
+    if on_gpu:
+        torch.cuda.synchronize()
+    if not multi:
+        return time.perf_counter()
+    t = torch.tensor([time.perf_counter() + lead_s], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    start = float(t.item())
+    if on_gpu:
+        torch.cuda.synchronize()
+    while time.perf_counter() < start:
+        pass
+    return max(start, time.perf_counter())
+
+
 def result_line(impl, value, ms, n_gpus, steps, warmup, clocks, e2e_value, h2d, d2h, gpu_launches, dtype,
                 extra_config=None):
     cfg = {"model": "MNIST ConvNet (train_dist.py Net, 21,840 params)", "global_batch": 128, "seq_len": None,

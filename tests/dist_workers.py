@@ -316,3 +316,23 @@ def w_one_node_guard(rank, size):
             raise AssertionError("multi-host symmetric world was not rejected")
     finally:
         socket.gethostname = real
+
+
+def w_aligned_start(rank, size):
+    """bench_common.aligned_start: every rank of a single-node job leaves at the same CLOCK_MONOTONIC instant, whatever the
+    skew with which the ranks arrive (rank 1 shows up 50 ms late)."""
+    import os
+    import sys
+    import time
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench_common import aligned_start
+    if rank == 1:
+        time.sleep(0.05)
+    t0 = aligned_start("cpu", lead_s=0.02)
+    left = time.perf_counter()
+    ts = [torch.zeros(2, dtype=torch.float64) for _ in range(size)]
+    dist.all_gather(ts, torch.tensor([t0, left], dtype=torch.float64))
+    starts = [float(t[0]) for t in ts]
+    assert max(starts) - min(starts) < 1e-3, starts          # the agreed instant (spin exit: microseconds; CI noise: < 1 ms)
+    assert all(float(t[1]) >= float(t[0]) for t in ts)

@@ -52,3 +52,11 @@ def test_reference_copy_is_byte_identical():
     else:
         ok, why = install_ref.verify()
     assert ok or "missing" in why, why
+
+
+def test_aligned_start_gives_every_rank_the_same_instant():
+    """The e2e window of both bench arms starts at a common instant (bench_common.aligned_start), gloo world 2 on the CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dist_tuto.pth_b200 as b2
+    import dist_workers as W
+    b2.launch(W.w_aligned_start, size=2, backend="gloo", join_timeout_s=120)
