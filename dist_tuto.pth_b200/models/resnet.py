@@ -70,7 +70,9 @@ class ResNet18(nn.Module):
         x = self.maxpool(F.relu(self.bn1(self.conv1(x)), inplace=True))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
-        if self.use_tc_fc and x.is_cuda and not torch.is_grad_enabled():
-            from ..ops.gemm import linear_bf16
-            return linear_bf16(x, self.fc.weight, self.fc.bias, out_dtype=torch.float32)
+        if self.use_tc_fc and x.is_cuda:
+            from ..ops.gemm import linear_bf16, linear_tc
+            if not torch.is_grad_enabled():
+                return linear_bf16(x, self.fc.weight, self.fc.bias, out_dtype=torch.float32)
+            return linear_tc(x.float(), self.fc.weight, self.fc.bias)     # trainable: dgrad + wgrad on the same tcgen05 kernel
         return self.fc(x)

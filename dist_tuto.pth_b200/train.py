@@ -14,7 +14,11 @@ Engines:
     path, BASELINE.json config #1; also runs on CUDA).
   * ``engine="fused"``  -- the B200 path: one fused sm_100a forward+backward
     kernel, one fused peer-memory all-reduce + SGD kernel, replayed as a CUDA
-    graph (``ops/convnet_fused.py``).  Default on CUDA.
+    graph (``ops/convnet_fused.py``).  Default on CUDA for per-GPU batches < 2048 (the reference's 128 // world).
+  * ``engine="batched"`` -- the throughput path for large per-GPU batches (BASELINE B1 "large-batch variant"): conv2
+    forward / data gradient / weight gradient and fc1 as implicit GEMMs on tcgen05 (``ops/convnet_batched.py``), same
+    fused exchange + SGD kernel.  ``auto`` picks it from 2048 samples per GPU up (measured: 1.1x the per-sample engine at
+    1024, 2.5x at 4096, 2.7x at 16384 -- profiles/REPORT_r2.md section 2).
 """
 from __future__ import annotations
 
@@ -34,7 +38,9 @@ from .utils import say
 from .utils.checkpoint import load_checkpoint, restore_optimizer, save_checkpoint
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
-__all__ = ["run", "train", "TrainConfig"]
+__all__ = ["run", "train", "TrainConfig", "BATCHED_FROM"]
+
+BATCHED_FROM = 2048      # per-GPU batch from which engine="auto" takes the batched tensor-core engine
 
 
 class TrainConfig:
@@ -66,8 +72,10 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     device = _pick_device(cfg)
     engine = cfg.engine
     if engine == "auto":
-        engine = "fused" if device.type == "cuda" else "torch"
-    fused_raw = engine == "fused" and (cfg.dataset is None or hasattr(cfg.dataset, "images"))
+        engine = "torch" if device.type != "cuda" else ("batched" if cfg.global_batch // max(size, 1) >= BATCHED_FROM else "fused")
+    if engine not in ("torch", "fused", "batched"):
+        raise ValueError(f"TrainConfig.engine must be auto / torch / fused / batched, got {engine!r}")
+    fused_raw = engine in ("fused", "batched") and (cfg.dataset is None or hasattr(cfg.dataset, "images"))
     train_set, bsz = partition_dataset(cfg.dataset, global_batch=cfg.global_batch, seed=cfg.seed,
                                        **({"raw_uint8": True} if fused_raw else {}))
     num_batches = ceil(len(train_set.dataset) / float(bsz))      # train_dist.py:112
@@ -80,6 +88,26 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
         if cfg.resume:
             start_steps = int(load_checkpoint(cfg.resume, trainer).get("steps", 0))
         step_fn, epoch_loss_fn, model = trainer.step, trainer.pop_loss_sum, trainer
+    elif engine == "batched":
+        from .ops.convnet_batched import BatchedTrainer
+        trainer = BatchedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
+                                 p_drop=cfg.p_drop, raw_uint8=fused_raw)
+        if cfg.resume:
+            start_steps = int(load_checkpoint(cfg.resume, trainer).get("steps", 0))
+        recycles = hasattr(train_set, "before_recycle")
+        if recycles:          # the loader's pinned staging buffers: a buffer is refilled only after its H2D copy has left it
+            def _oldest_step_done():
+                if copies_in_flight:
+                    copies_in_flight.popleft().synchronize()
+            train_set.before_recycle = _oldest_step_done
+
+        def step_fn(data, target):
+            trainer.step(data, target)
+            if recycles:
+                ev = torch.cuda.Event()
+                ev.record(trainer.stream)
+                copies_in_flight.append(ev)
+        epoch_loss_fn, model = trainer.pop_loss_sum, trainer
     else:
         model = Net(cfg.p_drop).to(device)
         if cfg.resume:

@@ -3,6 +3,7 @@
 
     python examples/train_mnist.py                       # CPU, gloo, world 2 (the reference default)
     python examples/train_mnist.py --backend b200 --size 8     # one process per B200, fused engine
+    python examples/train_mnist.py --backend b200 --size 8 --global-batch 32768   # large batch: tcgen05 batched engine
     torchrun --nproc-per-node 8 examples/train_mnist.py --backend b200 --external
 
 Prints ``Rank r, epoch e: mean loss`` per epoch like train_dist.py:125-127."""
@@ -18,7 +19,8 @@ import json  # noqa: E402
 
 def run(rank, size):
     CFG = json.loads(os.environ["B2_TRAIN_CFG"])          # spawned ranks re-import this file: pass the CLI through the env
-    cfg = dist.TrainConfig(epochs=CFG["epochs"], lr=CFG["lr"], max_steps=CFG["max_steps"], checkpoint=CFG["ckpt"])
+    cfg = dist.TrainConfig(epochs=CFG["epochs"], lr=CFG["lr"], max_steps=CFG["max_steps"], checkpoint=CFG["ckpt"],
+                           resume=CFG["resume"], global_batch=CFG["global_batch"], engine=CFG["engine"])
     out = dist.train(rank, size, cfg)
     if rank == 0:
         print(f"{out['steps']} steps, {out['samples_per_s']:.0f} samples/s (wall clock, whole job)")
@@ -32,9 +34,13 @@ if __name__ == "__main__":
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--checkpoint", default=None)
+    ap.add_argument("--resume", default=None)
+    ap.add_argument("--global-batch", type=int, default=128, help="split over the ranks (train_dist.py:85: 128 // world)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "torch", "fused", "batched"])
     ap.add_argument("--external", action="store_true", help="rank/size from torchrun/mpirun env")
     a = ap.parse_args()
-    os.environ["B2_TRAIN_CFG"] = json.dumps(dict(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint))
+    os.environ["B2_TRAIN_CFG"] = json.dumps(dict(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint, resume=a.resume,
+                                                 global_batch=a.global_batch, engine=a.engine))
     if a.external:
         dist.init_from_env(run, backend=a.backend)
     else:

@@ -180,6 +180,39 @@ def test_tcgen05_gemm_matches_torch(dev, M, N, K):
     assert torch.allclose(out_r.float(), ref.relu(), atol=6e-2, rtol=3e-2)
 
 
+@pytest.mark.parametrize("lead,K,N", [((256,), 320, 50), ((96,), 200, 10), ((8, 50), 512, 1000), ((1000,), 64, 64)])
+def test_tc_linear_forward_backward_on_tcgen05(dev, lead, K, N):
+    """`linear_tc`: forward, data gradient and weight gradient all on csrc/gemm_tcgen05.cu, vs the same op in fp32 on the same
+    bf16-rounded operands (the only differences left: accumulation order and the bf16 rounding of dY)."""
+    from dist_tuto.pth_b200.ops.gemm import TcLinear
+    g = torch.Generator().manual_seed(K + N)
+    m = TcLinear(K, N).to(dev)
+    x = torch.randn(*lead, K, generator=g).to(dev).requires_grad_()
+    gy = torch.randn(*lead, N, generator=g).to(dev)
+    y = m(x)
+    y.backward(gy)
+    xr = x.detach().to(torch.bfloat16).float().requires_grad_()
+    wr = m.weight.detach().to(torch.bfloat16).float().requires_grad_()
+    br = m.bias.detach().clone().requires_grad_()
+    yr = F.linear(xr, wr, br)
+    yr.backward(gy.to(torch.bfloat16).float())
+    for got, ref, name in ((y, yr, "y"), (x.grad, xr.grad, "dx"), (m.weight.grad, wr.grad, "dw")):
+        scale = float(ref.abs().max())
+        assert got.shape == ref.shape and float((got - ref).abs().max()) < 2e-3 * scale + 1e-5, (name, float((got - ref).abs().max()), scale)
+    assert torch.allclose(m.bias.grad, gy.reshape(-1, N).sum(0), atol=1e-3, rtol=1e-4)
+    # and it trains: a few SGD steps reduce a regression loss
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    tgt = torch.randn(*lead, N, generator=g).to(dev)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = F.mse_loss(m(x.detach()), tgt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+
+
 def test_train_loop_single_gpu_fused(dev):
     import dist_tuto.pth_b200 as b2
     from dist_tuto.pth_b200.data import SyntheticMNIST
@@ -191,6 +224,22 @@ def test_train_loop_single_gpu_fused(dev):
 
     b2.init_processes(0, 1, fn, backend="b200", master_port=b2.find_free_port())
     assert out["loss"][-1] < out["loss"][0] - 0.05, out["loss"]
+
+
+def test_train_loop_picks_the_batched_engine_for_large_batches(dev):
+    """train(): engine="auto" takes the tcgen05 batched engine from 2048 samples per GPU up (short tail batch included)."""
+    import dist_tuto.pth_b200 as b2
+    from dist_tuto.pth_b200.data import SyntheticMNIST
+    from dist_tuto.pth_b200.ops.convnet_batched import BatchedTrainer
+    ds = SyntheticMNIST(n=2048 * 3 + 500, seed=5)
+    out = {}
+
+    def fn(rank, size):
+        out.update(b2.train(rank, size, b2.TrainConfig(epochs=4, dataset=ds, lr=0.1, global_batch=2048, log=lambda *a: None)))
+
+    b2.init_processes(0, 1, fn, backend="b200", master_port=b2.find_free_port())
+    assert isinstance(out["model"], BatchedTrainer) and out["bsz"] == 2048 and out["steps"] == 16
+    assert out["loss"][-1] < out["loss"][0] - 0.02, out["loss"]
 
 
 @pytest.mark.parametrize("num_buffers,chunk,flags", [(6, 4, 0), (8, 2, 0), (12, 4, 1), (24, 8, 0), (7, 2, 0), (8, 1, 1), (24, 1, 1),
