@@ -396,14 +396,14 @@ class FusedTrainer:
             loader.begin_epoch()
         done, tail, finished = ex[0].run(-1 if max_steps is None else int(max_steps))
         self._nstep += done
-        if tail is not None:
-            ex[0].drain()
+        ex[0].drain()
+        if done:
+            self._last_loss_cum = ex[0].last_loss_cumulative()
+        if tail is not None:                     # the eager step reads the loss itself: it must come AFTER the executor's value
             self._eager_step(tail[0], tail[1], tail[1].numel())
             loader._l.release()
             done += 1
             finished = True                      # a short batch is always the last one of the epoch
-        ex[0].drain()
-        self._last_loss_cum = ex[0].last_loss_cumulative() if done else self._last_loss_cum
         return done, finished
 
     def pop_loss_sum(self) -> float:

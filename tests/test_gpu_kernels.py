@@ -262,6 +262,8 @@ def test_native_executor_matches_python_loop(dev, num_buffers, chunk, flags, mon
         if native:
             done, finished = tr.run_native(loader)
             assert done == 16 and finished
+            torch.cuda.synchronize()                      # the epoch ended with the eager short batch: its loss is the last one
+            assert tr.last_loss_cumulative() == float(tr.loss_acc[0].item())
             ex = tr._executors[id(loader)][0]
             k_eff = chunk
             while k_eff > 1 and max(4, num_buffers) < 3 * k_eff:
