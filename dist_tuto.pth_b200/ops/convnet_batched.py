@@ -11,7 +11,6 @@ Parity oracle: :mod:`.batched_reference` (plain PyTorch, same rounding points).
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, List, Optional
 
 import torch
