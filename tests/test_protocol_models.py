@@ -192,3 +192,142 @@ def test_flag_barrier_needs_the_monotonic_compare():
         if found:
             break
     assert found is not None and "deadlock" in found
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The generic LL all-reduce of csrc/allreduce.cu (`allreduce_ll_kernel`) shares its per-block call counter (the signal pad's
+# epoch word) with the barrier-based variants, and consecutive calls may have different sizes: a call only advances the
+# epochs of the blocks it launches, and only exchanges the vectors below its n_vec.  Claim (kernel comment): sender and
+# receiver of a line always agree on epoch and parity, and a line is never overwritten before its reader consumed it --
+# for ANY call sequence mixing LL calls of different sizes with barrier-type calls (one-shot / two-shot / NVLS / barrier
+# kernel advance a block's epoch by 1..3 and are full cross-rank barriers for that block).
+class LLRank:
+    """One rank executing a fixed call list in stream order: call k+1 starts after every thread of call k finished.  Inside a
+    call every vector (LL) / every block (barrier-type call) is its own thread of control: the GPU runs them concurrently,
+    so the scheduler may interleave them freely."""
+
+    def __init__(self, r, world, calls, nblocks, vec_per_block):
+        self.r, self.world, self.calls = r, world, calls
+        self.epoch = [0] * nblocks                      # per-block epoch word in this rank's signal pad
+        self.vpb = vec_per_block
+        self.k = -1
+        self.threads = {}                               # thread id -> pending atomic actions
+        self.bumps = []
+        self.next_call()
+
+    def next_call(self):
+        for b, ep in self.bumps:                        # barrier_epoch_store of the finished call
+            self.epoch[b] = ep
+        self.k += 1
+        self.threads, self.bumps = {}, []
+        if self.k >= len(self.calls):
+            return
+        kind, blocks, arg = self.calls[self.k]
+        if kind == "ll":                                # arg = n_vec: vectors v < n_vec, vector v lives in block v // vpb
+            for b in range(blocks):
+                vs = [v for v in range(b * self.vpb, (b + 1) * self.vpb) if v < arg]
+                if not vs:
+                    continue
+                ep = self.epoch[b] + 1
+                for v in vs:                            # per vector: store both half lines to every peer, then poll every peer
+                    acts = [("store", b, v, (self.r + i) % self.world, half, ep) for i in range(1, self.world) for half in (0, 1)]
+                    acts += [("poll", b, v, q, ep) for q in range(self.world) if q != self.r]
+                    self.threads[("v", v)] = acts
+                self.bumps.append((b, ep))
+        else:                                           # barrier-type call: arg = number of barrier rounds (1..3)
+            for b in range(blocks):
+                acts = []
+                for i in range(arg):
+                    acts += [("arrive", b, self.epoch[b] + 1 + i), ("wait", b, self.epoch[b] + 1 + i)]
+                self.threads[("b", b)] = acts
+                self.bumps.append((b, self.epoch[b] + arg))
+
+    def done(self):
+        return self.k >= len(self.calls)
+
+
+def run_ll(world, calls, nblocks, vpb, choose, max_ticks=400000, double_buffered=True):
+    cap = nblocks * vpb
+    par = (lambda ep: ep & 1) if double_buffered else (lambda ep: 0)
+    # inbox[dst][parity][src][v][half] = (payload, flag); flags[dst][block][src] = barrier epochs
+    inbox = [[[[[(None, 0), (None, 0)] for _ in range(cap)] for _ in range(world)] for _ in range(2)] for _ in range(world)]
+    flags = [[[0] * world for _ in range(nblocks)] for _ in range(world)]
+    ranks = [LLRank(r, world, calls, nblocks, vpb) for r in range(world)]
+    for _ in range(max_ticks):
+        for k in ranks:
+            while not k.done() and not k.threads:       # call finished (or launched nothing): stream order -> next call
+                k.next_call()
+        if all(k.done() for k in ranks):
+            return None
+        runnable = []
+        for k in ranks:
+            for tid, acts in k.threads.items():
+                a = acts[0]
+                if a[0] == "poll":
+                    _, b, v, q, ep = a
+                    line = inbox[k.r][par(ep)][q][v]
+                    ok = line[0][1] == ep and line[1][1] == ep
+                elif a[0] == "wait":
+                    _, b, ep = a
+                    ok = all(flags[k.r][b][q] >= ep for q in range(world) if q != k.r)
+                else:
+                    ok = True
+                if ok:
+                    runnable.append((k, tid))
+        if not runnable:
+            return "deadlock at calls %s" % [k.k for k in ranks]
+        k, tid = choose(runnable)
+        a = k.threads[tid].pop(0)
+        if not k.threads[tid]:
+            del k.threads[tid]
+        if a[0] == "store":
+            _, b, v, dst, half, ep = a
+            inbox[dst][par(ep)][k.r][v][half] = ((k.r, k.k, v, half), ep)
+        elif a[0] == "poll":
+            _, b, v, q, ep = a
+            line = inbox[k.r][par(ep)][q][v]
+            for half in (0, 1):
+                if line[half][0] != (q, k.k, v, half):
+                    return f"rank {k.r} call {k.k} consumed {line[half][0]} for (rank {q}, vector {v}, half {half})"
+        elif a[0] == "arrive":
+            _, b, ep = a
+            for q in range(world):
+                if q != k.r:
+                    flags[q][b][k.r] = ep
+    return "did not terminate"
+
+
+def _random_calls(rng, nblocks, vpb, n):
+    calls = []
+    for _ in range(n):
+        if rng.random() < 0.65:
+            n_vec = rng.randint(1, nblocks * vpb)
+            calls.append(("ll", (n_vec + vpb - 1) // vpb, n_vec))       # grid sized by the message, like b2_allreduce_launch
+        else:
+            calls.append(("bar", rng.randint(1, nblocks), rng.randint(1, 3)))
+    return calls
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_ll_allreduce_mixed_sizes_and_variants_are_safe(world):
+    nblocks, vpb = 3, 2
+    for seed in range(120):
+        rng = random.Random(seed * 104729 + world)
+        calls = _random_calls(rng, nblocks, vpb, 7)
+        weights = [rng.choice([1, 1, 5, 25]) for _ in range(world)]
+        bad = run_ll(world, calls, nblocks, vpb, lambda rs: rng.choices(rs, weights=[weights[k.r] for k, _ in rs])[0])
+        assert bad is None, (seed, calls, bad)
+
+
+def test_ll_model_catches_a_single_buffered_inbox():
+    """Negative control: without the parity double-buffer a fast rank's next call overwrites a line its peer is still polling
+    for (the peer then waits for an epoch that is gone) -- the model must find such a schedule."""
+    calls = [("ll", 2, 4)] * 4
+    found = None
+    for seed in range(300):
+        rng = random.Random(seed)
+        weights = [25, 1]
+        found = run_ll(2, calls, 2, 2, lambda rs: rng.choices(rs, weights=[weights[k.r] for k, _ in rs])[0], double_buffered=False)
+        if found:
+            break
+    assert found is not None and ("consumed" in found or "deadlock" in found), found
