@@ -156,9 +156,11 @@ def init_processes(rank: int, size: int, fn: Callable[[int, int], object], backe
         dist.init_process_group(**kw)
     try:
         if use_symm:
-            from .parallel import symm
-            assert_one_node(backend)
-            symm.init_world()
+            from .parallel import hier, symm
+            if _one_node():
+                symm.init_world()                  # one NVSwitch domain: every GPU maps every other GPU's memory
+            else:
+                hier.init_hier_world()             # several machines: peer memory inside each, NCCL rails across
         return fn(rank, size)
     finally:
         if teardown:
@@ -166,6 +168,16 @@ def init_processes(rank: int, size: int, fn: Callable[[int, int], object], backe
 
 
 init_process = init_processes  # BASELINE.json spelling
+
+
+def _one_node() -> bool:
+    """Collective: do all ranks of the default group sit on one machine?"""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return True
+    from .parallel.hier import hostname
+    hosts = [None] * dist.get_world_size()
+    dist.all_gather_object(hosts, hostname())
+    return len(set(hosts)) == 1
 
 
 def assert_one_node(backend: str = "b200") -> None:

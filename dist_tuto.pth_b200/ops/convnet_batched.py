@@ -108,6 +108,9 @@ class BatchedTrainer:
         if self.world > 1:
             from ..parallel import symm
             self.symm = symm.lookup_world(comm._g(group)) or symm.init_world(comm._g(group))
+            if not isinstance(self.symm, symm.SymmWorld):     # parallel/hier.HierWorld: the job spans several machines
+                raise RuntimeError("the fused gradient exchange runs inside ONE NVSwitch domain; on several machines use "
+                                   "train(engine='torch') / DistributedDataParallel (two-level all-reduce, parallel/hier.py)")
             self.grad_handle = self.symm.alloc(NPAR_ALLOC, torch.float32)
             self.grads = self.grad_handle.local
             self.grads.zero_()

@@ -56,6 +56,17 @@ class TrainConfig:
         self.checkpoint, self.resume = checkpoint, resume
 
 
+def _spans_machines() -> bool:
+    """True when the default group's world is the two-level one (launch.init_processes built it for a multi-machine job)."""
+    try:
+        from .parallel import symm
+        from .parallel.hier import HierWorld
+        w = symm.lookup_world(None)
+        return isinstance(w, HierWorld) and w.n_nodes > 1
+    except Exception:
+        return False
+
+
 def _pick_device(cfg: TrainConfig) -> torch.device:
     if cfg.device is not None:
         return torch.device(cfg.device)
@@ -71,8 +82,15 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     torch.manual_seed(cfg.seed)                                   # train_dist.py:105
     device = _pick_device(cfg)
     engine = cfg.engine
+    multi_node = _spans_machines()
     if engine == "auto":
-        engine = "torch" if device.type != "cuda" else ("batched" if cfg.global_batch // max(size, 1) >= BATCHED_FROM else "fused")
+        # several machines: the in-kernel gradient exchange of the fused engines is a single-NVSwitch-domain protocol, the
+        # bucketed engine reduces through the two-level world (parallel/hier.py)
+        engine = "torch" if (device.type != "cuda" or multi_node) else \
+            ("batched" if cfg.global_batch // max(size, 1) >= BATCHED_FROM else "fused")
+    if multi_node and engine in ("fused", "batched"):
+        raise ValueError(f"engine={engine!r} exchanges gradients inside one NVSwitch domain; this job spans several machines "
+                         "(use engine='auto' or 'torch')")
     if engine not in ("torch", "fused", "batched"):
         raise ValueError(f"TrainConfig.engine must be auto / torch / fused / batched, got {engine!r}")
     fused_raw = engine in ("fused", "batched") and (cfg.dataset is None or hasattr(cfg.dataset, "images"))

@@ -336,3 +336,39 @@ def w_aligned_start(rank, size):
     starts = [float(t[0]) for t in ts]
     assert max(starts) - min(starts) < 1e-3, starts          # the agreed instant (spin exit: microseconds; CI noise: < 1 ms)
     assert all(float(t[1]) >= float(t[0]) for t in ts)
+
+
+def w_hier_world(rank, size):
+    """parallel/hier.py: 4 ranks pretending to be 2 machines x 2 ranks.  Level 1 (inside a machine), level 2 (one rail per
+    local index, each reducing its slice across the machines) and the gather of the slices must add up to the global sum
+    x scale for tiny, evenly divisible and ragged messages; launch._one_node() must see two machines."""
+    import importlib
+    import os
+    import torch.distributed as dist
+    L = importlib.import_module("dist_tuto.pth_b200.launch")
+    from dist_tuto.pth_b200.parallel import hier, symm
+    os.environ["B200DIST_FAKE_HOSTNAME"] = f"n{rank // 2}"
+    try:
+        assert L._one_node() is False
+        w = hier.init_hier_world()
+        assert symm.lookup_world(None) is w and hier.init_hier_world() is w
+        d = w.describe()
+        assert d["nodes"] == 2 and d["ranks_per_node"] == 2 and d["node"] == rank // 2 and d["local_rank"] == rank % 2
+        assert w.nodes == [[0, 1], [2, 3]] and w.world == size
+        for n in (10, 8192, 5001, 4097):
+            g = torch.Generator().manual_seed(n)
+            base = torch.randn(size, n, generator=g)                  # row r = rank r's contribution (same on every rank)
+            t = base[rank].clone()
+            out = w.all_reduce_(t, scale=1.0 / size)
+            assert out.data_ptr() == t.data_ptr()
+            want = base.sum(0) / size
+            assert torch.allclose(t, want, atol=1e-5, rtol=1e-5), (n, float((t - want).abs().max()))
+        hd = w.alloc(100, torch.float32)                              # plain bucket on the CPU
+        assert hd.local.numel() == 128 and hd.local.dtype == torch.float32
+        from dist_tuto.pth_b200.train import _spans_machines
+        assert _spans_machines() is True
+    finally:
+        os.environ.pop("B200DIST_FAKE_HOSTNAME", None)
+        symm._WORLDS.pop(None, None)
+    assert L._one_node() is True                                      # real host names: one machine
+    dist.barrier()

@@ -118,3 +118,9 @@ def test_mpi_backend_without_a_launcher_environment_fails_loudly(monkeypatch):
 
 def test_symmetric_backend_refuses_to_span_machines():
     go(W.w_one_node_guard, 2)
+
+
+def test_two_level_world_over_simulated_machines():
+    """A multi-machine b200 job gets parallel/hier.HierWorld: peer memory inside a machine, one NCCL rail per local rank
+    across machines.  Here: gloo, 4 ranks on 2 simulated machines."""
+    go(W.w_hier_world, 4)
