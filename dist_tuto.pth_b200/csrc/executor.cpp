@@ -455,7 +455,7 @@ int64_t StepExecutor::run(int64_t max_steps, int* pending_slot, int64_t* pending
     cudaEventRecord(copied_[p], copy_);
     // kernels.  direct mode (default): plain stream launches with the programmatic-dependent-launch attribute -- the steps
     // chain on the device exactly as inside one long graph (a graph launch per step costs ~3 us of device time at every
-    // boundary: 31 vs 28 us per step, profiles/e2e_executor.json); graph mode: one 2-kernel graph per step.
+    // boundary: 31 vs 28 us per step, profiles/e2e/executor_variants_r2.json); graph mode: one 2-kernel graph per step.
     cudaStreamWaitEvent(compute_, copied_[p], 0);
     float* snap = cfg_.loss_hist != nullptr ? cfg_.loss_hist + 2 * p : nullptr;
     if (snap != nullptr) cudaStreamWaitEvent(compute_, loss_read_[p], 0);   // snapshot slot p was read back (two steps ago)
