@@ -8,6 +8,9 @@ process per rank (per GPU on the ``b200`` backend) with ``RANK`` / ``LOCAL_RANK`
 
 * the first rank that exits non-zero ends the job: the survivors are terminated (they would otherwise hang in a
   collective, SURVEY §5 "failure detection") and the launcher exits with that rank's code;
+* ``--max-restarts N``: after a failure the WHOLE job is started again (fresh rendezvous port, ``B200DIST_RESTART_COUNT`` =
+  1, 2, ... in the environment) up to N times -- a script that checkpoints (``TrainConfig(checkpoint=..., checkpoint_every=1)``)
+  and resumes when the file exists continues where the last checkpoint left off (``examples/train_mnist.py`` does);
 * ``--timeout`` bounds the whole job; ``SIGINT`` / ``SIGTERM`` are forwarded to every rank;
 * only the processes started here are ever signalled (exact PIDs).
 """
@@ -42,23 +45,38 @@ def _stop(procs: Sequence[subprocess.Popen], grace_s: float = 5.0) -> None:
 
 def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, master_addr: str = DEFAULT_ADDR,
                master_port: Optional[int] = None, timeout_s: Optional[float] = None, env: Optional[dict] = None,
-               poll_s: float = 0.1, nnodes: int = 1, node_rank: int = 0) -> int:
+               poll_s: float = 0.1, nnodes: int = 1, node_rank: int = 0, max_restarts: int = 0) -> int:
     """Run ``script`` as ``size`` local ranks; returns the job's exit code (0 = every rank exited 0).
 
     Multi-machine jobs (the tutorial's "replace MASTER_ADDR by the IP of the master", tuto.md:404-428): start the launcher
     once per machine with the same ``master_addr``/``master_port`` and ``nnodes``, and ``node_rank`` = 0..nnodes-1; global
-    rank = ``node_rank * size + local rank``.  (The ``b200`` backend's peer-memory world is one NVSwitch domain; use
-    ``nccl`` or ``gloo`` across machines.)
+    rank = ``node_rank * size + local rank``.  (Across machines the ``b200`` backend builds its two-level world,
+    parallel/hier.py: peer memory inside each machine, NCCL between them.)
 
-    Exit codes: the failing rank's own code; 124 on timeout (like ``timeout(1)``); 130 on interrupt."""
+    ``max_restarts``: how many times a failed job (a rank exited non-zero) is started over; the timeout covers all attempts.
+
+    Exit codes: the failing rank's own code (of the last attempt); 124 on timeout (like ``timeout(1)``); 130 on interrupt."""
     if nnodes > 1 and master_port is None:
         raise ValueError("multi-node jobs need an explicit master_port (the same on every node)")
     if not 0 <= node_rank < nnodes:
         raise ValueError("node_rank must be in [0, nnodes)")
+    deadline = None if timeout_s is None else time.monotonic() + timeout_s
+    attempt = 0
+    while True:
+        code, failed = _run_once(script, script_args, size, master_addr, master_port, deadline, timeout_s, env, poll_s, nnodes,
+                                 node_rank, attempt)
+        if not failed or attempt >= max_restarts:
+            return code
+        attempt += 1
+        sys.stderr.write(f"[dist_tuto.spawn] restarting the job (attempt {attempt + 1} of {max_restarts + 1})\n")
+
+
+def _run_once(script, script_args, size, master_addr, master_port, deadline, timeout_s, env, poll_s, nnodes, node_rank, attempt):
+    """One attempt; returns (exit code, restartable failure?)."""
     port = master_port or find_free_port(master_addr)
     base = dict(os.environ if env is None else env)
     base.update(WORLD_SIZE=str(size * nnodes), MASTER_ADDR=master_addr, MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(size),
-                GROUP_RANK=str(node_rank))
+                GROUP_RANK=str(node_rank), B200DIST_RESTART_COUNT=str(attempt))
     base.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, size))))
     procs: List[subprocess.Popen] = []
     interrupted = []
@@ -76,7 +94,6 @@ def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, mast
         for r in range(size):
             e = dict(base, RANK=str(node_rank * size + r), LOCAL_RANK=str(r))
             procs.append(subprocess.Popen([sys.executable, script, *script_args], env=e))
-        deadline = None if timeout_s is None else time.monotonic() + timeout_s
         while True:
             codes = [p.poll() for p in procs]
             bad = [(r, c) for r, c in enumerate(codes) if c not in (None, 0)]
@@ -84,17 +101,17 @@ def run_script(script: str, script_args: Sequence[str] = (), size: int = 2, mast
                 r, c = bad[0]
                 sys.stderr.write(f"[dist_tuto.spawn] rank {r} exited with code {c}; stopping the other ranks\n")
                 _stop(procs)
-                return c if c > 0 else 128 - c          # negative = killed by signal -c
+                return (c if c > 0 else 128 - c), True          # negative = killed by signal -c
             if all(c == 0 for c in codes):
-                return 0
+                return 0, False
             if interrupted:
                 sys.stderr.write("[dist_tuto.spawn] interrupted; stopping all ranks\n")
                 _stop(procs)
-                return 130
+                return 130, False
             if deadline is not None and time.monotonic() > deadline:
                 sys.stderr.write(f"[dist_tuto.spawn] job exceeded {timeout_s:.0f} s; stopping all ranks\n")
                 _stop(procs)
-                return 124
+                return 124, False
             time.sleep(poll_s)
     finally:
         _stop([p for p in procs if p.poll() is None])
@@ -111,11 +128,12 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ap.add_argument("--timeout", type=float, default=None, help="seconds for the whole job")
     ap.add_argument("--nnodes", type=int, default=1, help="machines in the job (run the launcher once per machine)")
     ap.add_argument("--node-rank", type=int, default=0, help="index of this machine, 0 = the one MASTER_ADDR points at")
+    ap.add_argument("--max-restarts", type=int, default=0, help="start the whole job over after a failure, up to N times")
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
     return run_script(a.script, a.script_args, size=a.size, master_addr=a.master_addr, master_port=a.master_port,
-                      timeout_s=a.timeout, nnodes=a.nnodes, node_rank=a.node_rank)
+                      timeout_s=a.timeout, nnodes=a.nnodes, node_rank=a.node_rank, max_restarts=a.max_restarts)
 
 
 if __name__ == "__main__":

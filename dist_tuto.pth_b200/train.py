@@ -49,11 +49,15 @@ class TrainConfig:
     def __init__(self, epochs: int = 10, lr: float = 0.01, momentum: float = 0.5, seed: int = 1234,
                  global_batch: int = 128, engine: str = "auto", device: Optional[str] = None,
                  max_steps: Optional[int] = None, dataset=None, log: Callable[..., None] = say,
-                 p_drop: float = 0.5, checkpoint: Optional[str] = None, resume: Optional[str] = None):
+                 p_drop: float = 0.5, checkpoint: Optional[str] = None, resume: Optional[str] = None,
+                 checkpoint_every: Optional[int] = None):
         self.epochs, self.lr, self.momentum, self.seed = epochs, lr, momentum, seed
         self.global_batch, self.engine, self.device = global_batch, engine, device
         self.max_steps, self.dataset, self.log, self.p_drop = max_steps, dataset, log, p_drop
-        self.checkpoint, self.resume = checkpoint, resume
+        # checkpoint: written by rank 0 at the end (and after every `checkpoint_every`-th epoch); resume: a checkpoint to start
+        # from -- parameters, momentum, step counter AND the number of completed epochs, so a resumed run does the remaining
+        # epochs with the shuffles those epochs would have had (restart after a failure: spawn.py --max-restarts)
+        self.checkpoint, self.resume, self.checkpoint_every = checkpoint, resume, checkpoint_every
 
 
 def _spans_machines() -> bool:
@@ -104,14 +108,16 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
         trainer = FusedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
                                p_drop=cfg.p_drop, raw_uint8=fused_raw)
         if cfg.resume:
-            start_steps = int(load_checkpoint(cfg.resume, trainer).get("steps", 0))
+            resume_blob = load_checkpoint(cfg.resume, trainer)
+            start_steps = int(resume_blob.get("steps", 0))
         step_fn, epoch_loss_fn, model = trainer.step, trainer.pop_loss_sum, trainer
     elif engine == "batched":
         from .ops.convnet_batched import BatchedTrainer
         trainer = BatchedTrainer(bsz, lr=cfg.lr, momentum=cfg.momentum, seed=cfg.seed, device=device,
                                  p_drop=cfg.p_drop, raw_uint8=fused_raw)
         if cfg.resume:
-            start_steps = int(load_checkpoint(cfg.resume, trainer).get("steps", 0))
+            resume_blob = load_checkpoint(cfg.resume, trainer)
+            start_steps = int(resume_blob.get("steps", 0))
         recycles = hasattr(train_set, "before_recycle")
         if recycles:          # the loader's pinned staging buffers: a buffer is refilled only after its H2D copy has left it
             def _oldest_step_done():
@@ -168,9 +174,16 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
             return v
 
     history, steps, t0 = [], 0, time.perf_counter()
+    start_epoch = 0
+    if resume_blob.get("in_progress"):            # a periodic checkpoint of an unfinished run: do the REMAINING epochs
+        start_epoch = min(int(resume_blob.get("epoch", 0)), cfg.epochs)
+        history = list(resume_blob.get("history", []))[:start_epoch]
+    # (a checkpoint of a finished run starts a new run of cfg.epochs epochs from its parameters / momentum / step counter)
+    if start_epoch and hasattr(train_set, "_epoch"):
+        train_set._epoch = start_epoch                                    # the loader shuffles by (seed, epoch index)
     done = False
     native_loop = engine == "fused" and hasattr(train_set, "begin_epoch") and torch.cuda.is_available()
-    for epoch in range(cfg.epochs):
+    for epoch in range(start_epoch, cfg.epochs):
         model.train()
         nb = 0
         copies_in_flight.clear()          # the previous epoch ended with a device sync (epoch_loss_fn): nothing is pending
@@ -193,9 +206,17 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
         cfg.log("Rank ", comm.get_rank(), ", epoch ", epoch, ": ", mean_loss)
         if done:
             break
+        epochs_done = epoch + 1
+        if cfg.checkpoint and cfg.checkpoint_every and epochs_done % cfg.checkpoint_every == 0 and epochs_done < cfg.epochs:
+            if comm.get_rank() == 0:
+                save_checkpoint(cfg.checkpoint, model, optimizer=optimizer, steps=start_steps + steps, history=history,
+                                epoch=epochs_done, in_progress=True)
+            if size > 1:
+                comm.barrier()                   # nobody runs ahead into a failure before the checkpoint is on disk
     elapsed = time.perf_counter() - t0
     if cfg.checkpoint and comm.get_rank() == 0:
-        save_checkpoint(cfg.checkpoint, model, optimizer=optimizer, steps=start_steps + steps, history=history)
+        save_checkpoint(cfg.checkpoint, model, optimizer=optimizer, steps=start_steps + steps, history=history,
+                        epoch=max(0, len(history) - (1 if done else 0)), in_progress=False)
     return {"loss": history, "steps": steps, "seconds": elapsed, "bsz": bsz,
             "samples_per_s": steps * bsz * size / max(elapsed, 1e-9), "model": model}
 

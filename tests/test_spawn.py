@@ -66,3 +66,21 @@ def test_multi_node_needs_an_explicit_port():
     from dist_tuto.pth_b200.spawn import run_script
     with pytest.raises(ValueError, match="master_port"):
         run_script(SCRIPT, ["allreduce"], size=1, nnodes=2, node_rank=0)
+
+
+def test_restart_after_a_failure_resumes_from_the_last_checkpoint(tmp_path):
+    """--max-restarts: rank 0 dies at the end of epoch 1 of 3 on the first attempt (before checkpointing it); the second attempt
+    resumes from the checkpoint written after epoch 0 (TrainConfig.checkpoint_every) and runs exactly the two remaining epochs."""
+    import torch
+    ckpt = str(tmp_path / "job.pt")
+    p, _ = launch("--size", "2", "--max-restarts", "1", SCRIPT, "train_restart", ckpt)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "rank 0 exited with code 9" in p.stderr and "restarting the job (attempt 2 of 2)" in p.stderr
+    blob = torch.load(ckpt, map_location="cpu")
+    nb = 512 // 2 // 64                                     # 2 ranks x batch 64: 4 steps per epoch
+    assert blob["epoch"] == 3 and blob["in_progress"] is False and len(blob["history"]) == 3 and blob["steps"] == 3 * nb
+    notes = open(ckpt + ".epochs").read().strip().splitlines()
+    assert notes == ["attempt 1: epochs [1, 2] history 3"], notes          # attempt 0 never finished; attempt 1 did epochs 1 and 2
+    # without restarts the same failure ends the job with the rank's exit code
+    p2, _ = launch("--size", "2", SCRIPT, "train_restart", str(tmp_path / "job2.pt"))
+    assert p2.returncode == 9
