@@ -363,6 +363,36 @@ def w_hier_world(rank, size):
             assert out.data_ptr() == t.data_ptr()
             want = base.sum(0) / size
             assert torch.allclose(t, want, atol=1e-5, rtol=1e-5), (n, float((t - want).abs().max()))
+        # the CUDA branch (level 1 = a SymmWorld over the machine's ranks) with a stand-in that has SymmWorld's call shape
+        class FakeLocal:
+            multicast = False
+            calls = []
+
+            def __init__(self, group):
+                self.group = group
+
+            def supports(self, t):
+                return t.is_contiguous()
+
+            def all_reduce_(self, t, scale=1.0, handle=None, variant=None, wire=None, max_blocks=None):
+                FakeLocal.calls.append((t.numel(), scale, handle, max_blocks))
+                dist.all_reduce(t, group=self.group)
+                t.mul_(scale)
+                return t
+
+            def alloc(self, numel, dtype):
+                return ("symmetric", numel, dtype)
+
+            def describe(self):
+                return {"world": 2}
+
+        w.local = FakeLocal(w.local_group)
+        base = torch.arange(size * 6000, dtype=torch.float32).view(size, 6000)
+        t = base[rank].clone()
+        w.all_reduce_(t, scale=0.25, handle="H", max_blocks=7)
+        assert torch.allclose(t, base.sum(0) * 0.25) and FakeLocal.calls == [(6000, 0.25, "H", 7)]
+        assert w.alloc(10, torch.float32) == ("symmetric", 10, torch.float32) and w.describe()["local"] == {"world": 2}
+        w.local = None
         hd = w.alloc(100, torch.float32)                              # plain bucket on the CPU
         assert hd.local.numel() == 128 and hd.local.dtype == torch.float32
         from dist_tuto.pth_b200.train import _spans_machines
