@@ -36,6 +36,7 @@ from .models.convnet import Net
 from .ops.optim import FlatSGD
 from .utils import say
 from .utils.checkpoint import load_checkpoint, restore_optimizer, save_checkpoint
+from .utils.trace import NullTracer, Tracer
 from .parallel.ddp import GradBucket, average_gradients, broadcast_parameters
 
 __all__ = ["run", "train", "TrainConfig", "BATCHED_FROM"]
@@ -50,7 +51,7 @@ class TrainConfig:
                  global_batch: int = 128, engine: str = "auto", device: Optional[str] = None,
                  max_steps: Optional[int] = None, dataset=None, log: Callable[..., None] = say,
                  p_drop: float = 0.5, checkpoint: Optional[str] = None, resume: Optional[str] = None,
-                 checkpoint_every: Optional[int] = None):
+                 checkpoint_every: Optional[int] = None, trace: Optional[str] = None):
         self.epochs, self.lr, self.momentum, self.seed = epochs, lr, momentum, seed
         self.global_batch, self.engine, self.device = global_batch, engine, device
         self.max_steps, self.dataset, self.log, self.p_drop = max_steps, dataset, log, p_drop
@@ -58,6 +59,9 @@ class TrainConfig:
         # from -- parameters, momentum, step counter AND the number of completed epochs, so a resumed run does the remaining
         # epochs with the shuffles those epochs would have had (restart after a failure: spawn.py --max-restarts)
         self.checkpoint, self.resume, self.checkpoint_every = checkpoint, resume, checkpoint_every
+        # trace: path of a Chrome / Perfetto trace (utils/trace.py) -- host spans per epoch / step phase and one device span per
+        # step (torch engine) or per epoch (fused engines: their steps are launched by C++ / CUDA graphs), all ranks in one file
+        self.trace = trace
 
 
 def _spans_machines() -> bool:
@@ -86,6 +90,7 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     torch.manual_seed(cfg.seed)                                   # train_dist.py:105
     device = _pick_device(cfg)
     engine = cfg.engine
+    tracer = Tracer(rank) if cfg.trace else NullTracer()
     multi_node = _spans_machines()
     if engine == "auto":
         # several machines: the in-kernel gradient exchange of the fused engines is a single-NVSwitch-domain protocol, the
@@ -154,19 +159,25 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
             train_set.before_recycle = _oldest_copy_done
 
         def step_fn(data, target):
-            data = data.to(device, non_blocking=True)
-            target = target.to(device, non_blocking=True)
-            if device.type == "cuda" and hasattr(train_set, "before_recycle"):
-                ev = torch.cuda.Event()
-                ev.record()
-                copies_in_flight.append(ev)
-            optimizer.zero_grad()                                # buckets were re-zeroed by the previous step()
-            output = model(data)
-            loss = F.nll_loss(output, target)
-            acc.add_(loss.detach())                              # epoch_loss += loss (D4 fixed)
-            loss.backward()
-            average_gradients(model)
-            optimizer.step()
+            with tracer.device_span("step", cat="step"):
+                with tracer.span("h2d"):
+                    data = data.to(device, non_blocking=True)
+                    target = target.to(device, non_blocking=True)
+                if device.type == "cuda" and hasattr(train_set, "before_recycle"):
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    copies_in_flight.append(ev)
+                optimizer.zero_grad()                                # buckets were re-zeroed by the previous step()
+                with tracer.span("forward + loss"):
+                    output = model(data)
+                    loss = F.nll_loss(output, target)
+                    acc.add_(loss.detach())                          # epoch_loss += loss (D4 fixed)
+                with tracer.span("backward"):
+                    loss.backward()
+                with tracer.span("average_gradients"):
+                    average_gradients(model)
+                with tracer.span("optimizer"):
+                    optimizer.step()
 
         def epoch_loss_fn():
             v = float(acc.item())
@@ -187,21 +198,31 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
         model.train()
         nb = 0
         copies_in_flight.clear()          # the previous epoch ended with a device sync (epoch_loss_fn): nothing is pending
-        if native_loop:       # C++ executor: prefetch thread -> cudaGraphLaunch per step, no Python in the loop
-            budget = None if cfg.max_steps is None else cfg.max_steps - steps
-            nb, _ = trainer.run_native(train_set, max_steps=budget)
-            steps += nb
-            done = cfg.max_steps is not None and steps >= cfg.max_steps
-        else:
-            for data, target in train_set:
-                step_fn(data, target)
-                steps += 1
-                nb += 1
-                if cfg.max_steps is not None and steps >= cfg.max_steps:
-                    done = True
-                    break
-        denom = num_batches if not done else max(nb, 1)
-        mean_loss = epoch_loss_fn() / denom
+        with tracer.span(f"epoch {epoch}", cat="epoch", engine=engine):
+            if native_loop:       # C++ executor: prefetch thread -> cudaGraphLaunch per step, no Python in the loop
+                budget = None if cfg.max_steps is None else cfg.max_steps - steps
+                with tracer.span("run_native (C++ executor: the whole epoch, returns drained)", cat="step"):
+                    nb, _ = trainer.run_native(train_set, max_steps=budget)
+                steps += nb
+                done = cfg.max_steps is not None and steps >= cfg.max_steps
+            else:
+                batches = iter(train_set)
+                while True:
+                    with tracer.span("next batch", cat="data"):
+                        item = next(batches, None)
+                    if item is None:
+                        break
+                    step_fn(*item)
+                    steps += 1
+                    nb += 1
+                    if cfg.max_steps is not None and steps >= cfg.max_steps:
+                        done = True
+                        batches.close() if hasattr(batches, "close") else None     # run the loader's clean-up (stops its thread)
+                        break
+            denom = num_batches if not done else max(nb, 1)
+            with tracer.span("read epoch loss (device sync)", cat="sync"):
+                loss_sum = epoch_loss_fn()
+        mean_loss = loss_sum / denom
         history.append(mean_loss)
         cfg.log("Rank ", comm.get_rank(), ", epoch ", epoch, ": ", mean_loss)
         if done:
@@ -217,8 +238,9 @@ def train(rank: int, size: int, cfg: Optional[TrainConfig] = None):
     if cfg.checkpoint and comm.get_rank() == 0:
         save_checkpoint(cfg.checkpoint, model, optimizer=optimizer, steps=start_steps + steps, history=history,
                         epoch=max(0, len(history) - (1 if done else 0)), in_progress=False)
+    trace_file = tracer.save(cfg.trace) if cfg.trace else None          # collective: rank 0 writes every rank's rows
     return {"loss": history, "steps": steps, "seconds": elapsed, "bsz": bsz,
-            "samples_per_s": steps * bsz * size / max(elapsed, 1e-9), "model": model}
+            "samples_per_s": steps * bsz * size / max(elapsed, 1e-9), "model": model, "trace": trace_file}
 
 
 def run(rank: int, size: int):

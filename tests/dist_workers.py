@@ -402,3 +402,30 @@ def w_hier_world(rank, size):
         symm._WORLDS.pop(None, None)
     assert L._one_node() is True                                      # real host names: one machine
     dist.barrier()
+
+
+def w_train_trace(rank, size):
+    """TrainConfig(trace=...): one Chrome trace with a process row per rank, epoch spans containing step-phase spans."""
+    import json
+    import os
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f"b2_trace_{os.environ.get('MASTER_PORT', '0')}.json")
+    out = b2.train(rank, size, b2.TrainConfig(epochs=2, dataset=SyntheticMNIST(n=512, seed=1), engine="torch", device="cpu",
+                                              log=lambda *a: None, trace=path))
+    assert (out["trace"] == path) == (rank == 0)
+    if rank == 0:
+        ev = json.load(open(path))["traceEvents"]
+        os.remove(path)
+        assert {e["pid"] for e in ev} == set(range(size))
+        assert sorted(e["args"]["name"] for e in ev if e["ph"] == "M") == [f"rank {r}" for r in range(size)]
+        for r in range(size):
+            mine = [e for e in ev if e["pid"] == r and e["ph"] == "X"]
+            epochs = [e for e in mine if e["cat"] == "epoch"]
+            assert [e["name"] for e in epochs] == ["epoch 0", "epoch 1"] and epochs[0]["args"]["engine"] == "torch"
+            nb = 512 // size // (128 // size)
+            for name in ("h2d", "forward + loss", "backward", "average_gradients", "optimizer", "step"):
+                spans = [e for e in mine if e["name"] == name]
+                assert len(spans) == 2 * nb, (name, len(spans))
+                for e in spans:                                  # every step phase lies inside one of the two epoch spans
+                    assert any(ep["ts"] <= e["ts"] and e["ts"] + e["dur"] <= ep["ts"] + ep["dur"] + 1 for ep in epochs), name
+            assert len([e for e in mine if e["name"] == "next batch"]) == 2 * (nb + 1)     # + the exhausted fetch of each epoch

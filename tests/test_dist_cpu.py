@@ -124,3 +124,7 @@ def test_two_level_world_over_simulated_machines():
     """A multi-machine b200 job gets parallel/hier.HierWorld: peer memory inside a machine, one NCCL rail per local rank
     across machines.  Here: gloo, 4 ranks on 2 simulated machines."""
     go(W.w_hier_world, 4)
+
+
+def test_train_writes_one_trace_for_all_ranks():
+    go(W.w_train_trace, 2)
