@@ -26,7 +26,7 @@ def run(rank, size):
         resume = CFG["ckpt"]                              # restarted by the launcher: continue from our own last checkpoint
     cfg = dist.TrainConfig(epochs=CFG["epochs"], lr=CFG["lr"], max_steps=CFG["max_steps"], checkpoint=CFG["ckpt"],
                            checkpoint_every=CFG["ckpt_every"], resume=resume, global_batch=CFG["global_batch"],
-                           engine=CFG["engine"])
+                           engine=CFG["engine"], trace=CFG["trace"])
     out = dist.train(rank, size, cfg)
     if rank == 0:
         print(f"{out['steps']} steps, {out['samples_per_s']:.0f} samples/s (wall clock, whole job)")
@@ -42,11 +42,12 @@ if __name__ == "__main__":
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--checkpoint-every", type=int, default=None, help="also checkpoint after every N-th epoch")
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--trace", default=None, help="write a Chrome / Perfetto trace of all ranks to this file")
     ap.add_argument("--global-batch", type=int, default=128, help="split over the ranks (train_dist.py:85: 128 // world)")
     ap.add_argument("--engine", default="auto", choices=["auto", "torch", "fused", "batched"])
     ap.add_argument("--external", action="store_true", help="rank/size from torchrun/mpirun env")
     a = ap.parse_args()
-    os.environ["B2_TRAIN_CFG"] = json.dumps(dict(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint, ckpt_every=a.checkpoint_every, resume=a.resume,
+    os.environ["B2_TRAIN_CFG"] = json.dumps(dict(epochs=a.epochs, lr=a.lr, max_steps=a.max_steps, ckpt=a.checkpoint, ckpt_every=a.checkpoint_every, resume=a.resume, trace=a.trace,
                                                  global_batch=a.global_batch, engine=a.engine))
     if a.external:
         dist.init_from_env(run, backend=a.backend)
